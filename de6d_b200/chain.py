@@ -1,0 +1,274 @@
+"""The SA + NMS op chain of BASELINE.json, built only from this package's ops.
+
+It is the sequence of hot-path calls one Det6D / SASA inference forward makes on a batch of frames
+(SURVEY.md section 3.1): per SA layer  FPS (D / F / S) -> gather_operation -> per radius scale
+ball_query_cnt -> grouping_operation(xyz) -> centre subtraction -> grouping_operation(features) -> concat,
+then the head's vote-centre grouping and the rotated NMS over the frame's proposals.  The learned parts in
+between (shared MLPs, vote / box regression) are out of this path's scope; their outputs -- per-layer
+features, S-FPS scores, proposals -- are synthetic inputs of the right shape (de6d_b200.synth).
+
+Data dependencies follow the real network: F-FPS / S-FPS of layer k+1 wait for the groupings of layer k (they
+consume features / scores computed from them), D-FPS of layer k+1 only needs layer k's sampled coordinates and
+overlaps with layer k's grouping on a side stream.  The whole step is captured once into a CUDA graph.
+
+Layer shapes: the reference ships no YAML; the defaults below are the SASA/3DSSD shapes named
+in BASELINE.json configs[1] (16384 -> 4096 -> 1024 -> 512, 256 vote centres) and are plain parameters.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import pointnet2_utils as pu
+from .iou3d_nms_utils import BatchedNMS
+
+
+@dataclass
+class SALayer:
+    npoints: Tuple[int, ...]                  # points sampled by each method
+    methods: Tuple[str, ...]                  # 'd-fps' | 'f-fps' | 's-fps'
+    ranges: Tuple[Tuple[int, int], ...]       # slice of the layer input each method samples from
+    radii: Tuple[float, ...]
+    nsamples: Tuple[int, ...]
+    c_in: int                                 # feature channels entering the layer
+
+
+@dataclass
+class ChainConfig:
+    n_points: int = 16384
+    layers: List[SALayer] = field(default_factory=lambda: [
+        SALayer((4096,), ('d-fps',), ((0, 16384),), (0.2, 0.4, 0.8), (32, 32, 64), 1),
+        SALayer((512, 512), ('f-fps', 'd-fps'), ((0, 4096), (0, 4096)), (0.4, 0.8, 1.6), (32, 32, 64), 64),
+        SALayer((256, 256), ('s-fps', 'd-fps'), ((0, 512), (512, 1024)), (1.6, 3.2, 4.8), (32, 32, 32), 128),
+    ])
+    n_votes: int = 256
+    vote_radii: Tuple[float, ...] = (4.8, 6.4)
+    vote_nsamples: Tuple[int, ...] = (16, 32)
+    vote_c_in: int = 256
+    n_proposals: int = 512
+    nms_thresh: float = 0.01
+    ffps_gamma: float = 1.0
+
+    def name(self):
+        return "sasa-3dssd-chain-%d" % self.n_points
+
+
+def small_config():
+    """A few-thousand-point version for tests and smoke()."""
+    return ChainConfig(
+        n_points=2048,
+        layers=[
+            SALayer((512,), ('d-fps',), ((0, 2048),), (0.8, 1.6), (16, 32), 1),
+            SALayer((128, 128), ('f-fps', 'd-fps'), ((0, 512), (0, 512)), (1.6, 3.2), (16, 32), 16),
+            SALayer((64, 64), ('s-fps', 'd-fps'), ((0, 128), (128, 256)), (3.2, 4.8), (16, 16), 32),
+        ],
+        n_votes=64, vote_radii=(4.8,), vote_nsamples=(16,), vote_c_in=32, n_proposals=128)
+
+
+def make_inputs(cfg: ChainConfig, batch: int, seed: int = 0, pinned: bool = True):
+    """Host-side inputs of one step (numpy-seeded, identical on every machine)."""
+    from . import synth
+    import numpy as np
+    xyz = synth.clouds(batch, cfg.n_points, seed)
+    feats = [synth.features(batch, cfg.layers[0].c_in, cfg.n_points, seed)]
+    n_in = cfg.n_points
+    scores = []
+    for li, layer in enumerate(cfg.layers):
+        n_out = sum(layer.npoints)
+        if li + 1 < len(cfg.layers):
+            feats.append(synth.features(batch, cfg.layers[li + 1].c_in, n_out, seed + 10 * (li + 1)))
+        scores.append(synth.weights(batch, n_in, seed + 77 + li))   # S-FPS weights = sigmoid(score) ** gamma
+        n_in = n_out
+    vote_feats = synth.features(batch, cfg.vote_c_in, n_in, seed + 99)
+    vote_offsets = np.random.default_rng(seed + 5).normal(0, 0.5, size=(batch, cfg.n_votes, 3)).astype(np.float32)
+    boxes, box_scores = synth.proposals(batch, cfg.n_proposals, seed)
+    host = {"xyz": xyz, "vote_feats": vote_feats, "vote_offsets": vote_offsets, "boxes": boxes, "box_scores": box_scores}
+    for i, f in enumerate(feats):
+        host["feats%d" % i] = f
+    for i, s in enumerate(scores):
+        host["scores%d" % i] = s
+    out = {}
+    for k, v in host.items():
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        out[k] = t.pin_memory() if pinned and torch.cuda.is_available() else t
+    return out
+
+
+class OpChain:
+    """One process, one GPU, `batch` frames per step.
+
+        chain = OpChain(cfg, batch)                 # allocates static device buffers
+        out = chain.step_host(host_inputs)          # H2D -> graph replay -> D2H, returns host tensors
+        chain.load(host_inputs); chain.step()       # device-resident step (inputs already in HBM)
+    """
+
+    N_SIDE = 4
+
+    def __init__(self, cfg: ChainConfig, batch: int, device: Optional[torch.device] = None, use_graph: bool = True,
+                 keep_matrices: bool = False):
+        self.cfg, self.batch = cfg, batch
+        self.keep_matrices = keep_matrices   # tests: expose the F-FPS distance matrices fed to the kernel
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.use_graph = use_graph
+        self.main = torch.cuda.Stream(self.device)
+        self.side = [torch.cuda.Stream(self.device) for _ in range(self.N_SIDE)]   # grouping, one per scale
+        self.samp = [torch.cuda.Stream(self.device) for _ in range(2)]             # extra sampling methods
+        self.inputs = None          # static device copies
+        self.outputs = None         # static device outputs of the last captured step
+        self.graph = None
+        self.host_out = None
+        self.kernels_per_step = None
+        self.nms = None
+
+    # ---- buffers ------------------------------------------------------------------------------------
+    def _alloc_like(self, host):
+        with torch.cuda.device(self.device):
+            self.inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            self.nms = BatchedNMS(self.batch, self.cfg.n_proposals, device=self.device)
+
+    def load(self, host, stream=None):
+        if self.inputs is None:
+            self._alloc_like(host)
+        s = stream or self.main
+        with torch.cuda.stream(s):
+            for k, v in host.items():
+                self.inputs[k].copy_(v, non_blocking=True)
+
+    def h2d_bytes(self):
+        return sum(v.numel() * v.element_size() for v in self.inputs.values())
+
+    # ---- the chain --------------------------------------------------------------------------------
+    def _group_scales(self, xyz, new_xyz, feats, radii, nsamples, after, outs, tag):
+        """One QueryWithCntAndGroup per radius scale, scales spread over the side streams."""
+        done = []
+        for si, (r, ns) in enumerate(zip(radii, nsamples)):
+            st = self.side[si % self.N_SIDE]
+            st.wait_event(after)
+            with torch.cuda.stream(st):
+                idx_cnt, idx = pu.ball_query_cnt(r, ns, xyz, new_xyz)
+                xyz_t = xyz.transpose(1, 2).contiguous()
+                g_xyz = pu.grouping_operation(xyz_t, idx)
+                g_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
+                g_feat = pu.grouping_operation(feats, idx)
+                new_features = torch.cat([g_xyz, g_feat], dim=1)
+                outs["%s_s%d_cnt" % (tag, si)] = idx_cnt
+                outs["%s_s%d" % (tag, si)] = new_features
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        return done
+
+    def _forward(self):
+        cfg, inp = self.cfg, self.inputs
+        outs = {}
+        main = self.main
+        xyz = inp["xyz"]
+        grouped_done: List[torch.cuda.Event] = []
+        pending: List[torch.cuda.Event] = []   # every side-stream event main has not joined yet
+        with torch.cuda.stream(main):
+            for li, layer in enumerate(cfg.layers):
+                feats = inp["feats%d" % li]
+                scores = inp["scores%d" % li]
+                start = torch.cuda.Event()
+                start.record(main)
+                idx_parts = [None] * len(layer.methods)
+                joins = []
+                for mi, (method, npnt, (lo, hi)) in enumerate(zip(layer.methods, layer.npoints, layer.ranges)):
+                    st = main if mi == 0 else self.samp[(mi - 1) % len(self.samp)]
+                    if st is not main:
+                        st.wait_event(start)
+                    needs_prev_features = method in ("f-fps", "s-fps")
+                    with torch.cuda.stream(st):
+                        if needs_prev_features:
+                            for ev in grouped_done:
+                                st.wait_event(ev)
+                        xyz_slice = xyz[:, lo:hi, :].contiguous()
+                        if method == "d-fps":
+                            sidx = pu.furthest_point_sample(xyz_slice, npnt)
+                        elif method == "f-fps":
+                            f_slice = feats[:, :, lo:hi].permute(0, 2, 1)
+                            mat = pu.calc_dist_matrix_for_sampling(xyz_slice, f_slice, cfg.ffps_gamma)
+                            sidx = pu.furthest_point_sample_matrix(mat, npnt)
+                            if self.keep_matrices:
+                                outs["l%d_ffps_matrix" % li] = mat
+                        elif method == "s-fps":
+                            w = scores[:, lo:hi].contiguous()   # already sigmoid(score) ** gamma (caller side)
+                            sidx = pu.furthest_point_sample_weights(xyz_slice, w, npnt)
+                        else:
+                            raise NotImplementedError(method)
+                        idx_parts[mi] = sidx + lo
+                        idx_parts[mi].record_stream(main)
+                        if st is not main:
+                            ev = torch.cuda.Event()
+                            ev.record(st)
+                            joins.append(ev)
+                for ev in joins:
+                    main.wait_event(ev)
+                sample_idx = torch.cat(idx_parts, dim=-1)
+                xyz_flipped = xyz.transpose(1, 2).contiguous()
+                new_xyz = pu.gather_operation(xyz_flipped, sample_idx).transpose(1, 2).contiguous()
+                outs["l%d_idx" % li] = sample_idx
+                sampled = torch.cuda.Event()
+                sampled.record(main)
+                grouped_done = self._group_scales(xyz, new_xyz, feats, layer.radii, layer.nsamples, sampled, outs, "l%d" % li)
+                pending.extend(grouped_done)
+                xyz = new_xyz
+            # head: vote centres grouped over the last layer's points (after its features exist)
+            for ev in pending:
+                main.wait_event(ev)
+            votes = (xyz[:, :cfg.n_votes, :] + inp["vote_offsets"]).contiguous()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            head_done = self._group_scales(xyz, votes, inp["vote_feats"], cfg.vote_radii, cfg.vote_nsamples, ready, outs, "head")
+            for ev in head_done:
+                main.wait_event(ev)
+            keep, num = self.nms(inp["boxes"], inp["box_scores"], cfg.nms_thresh)
+            outs["nms_keep"], outs["nms_num"] = keep, num
+        return outs
+
+    def capture(self):
+        """Warm up eagerly once (sets kernel attributes, fills allocator pools), then capture the graph."""
+        assert self.inputs is not None, "call load() first"
+        from ._lib import launch_count
+        with torch.cuda.device(self.device):
+            c0 = launch_count()
+            self.outputs = self._forward()
+            self.kernels_per_step = launch_count() - c0
+            torch.cuda.synchronize(self.device)
+            if self.use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=self.main):
+                    self.outputs = self._forward()
+                torch.cuda.synchronize(self.device)
+            res = self.result_tensors()
+            self.host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in res.items()}
+
+    def step(self):
+        """One pass over the batch with inputs already resident in HBM (enqueue only, no sync)."""
+        if self.graph is not None:
+            with torch.cuda.stream(self.main):
+                self.graph.replay()
+        else:
+            self.outputs = self._forward()
+
+    def result_tensors(self):
+        """What a caller reads back per step: sampled indices of the last layer and the detections kept."""
+        last = len(self.cfg.layers) - 1
+        return {"sample_idx": self.outputs["l%d_idx" % last], "nms_keep": self.outputs["nms_keep"],
+                "nms_num": self.outputs["nms_num"]}
+
+    def d2h_bytes(self):
+        return sum(v.numel() * v.element_size() for v in self.result_tensors().values())
+
+    def step_host(self, host, sync=True):
+        """Public end-to-end call: pinned host inputs -> device, run, results -> pinned host."""
+        self.load(host)
+        if self.graph is None and self.outputs is None:
+            self.capture()
+        self.step()
+        with torch.cuda.stream(self.main):
+            for k, v in self.result_tensors().items():
+                self.host_out[k].copy_(v, non_blocking=True)
+        if sync:
+            self.main.synchronize()
+        return self.host_out

@@ -1,0 +1,69 @@
+// Shared device helpers for the de6d_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DE6D_OK 0
+#define DE6D_ERR_INVALID 1   // bad argument (negative size, null pointer, unsupported shape)
+#define DE6D_ERR_CUDA 2      // a CUDA runtime call or launch failed (see de6d_last_error_string)
+
+namespace de6d {
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Squared distance exactly as the reference's nvcc build evaluates
+//   (ax-bx)*(ax-bx) + (ay-by)*(ay-by) + (az-bz)*(az-bz)
+// (sampling_gpu.cu:143, ball_query_gpu.cu:39, interpolate_gpu.cu:41): the y product is a plain rounded
+// FMUL, x and z are FFMAs.  Spelled with intrinsics so no other contraction can happen.
+__device__ __forceinline__ float sqdist(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// Monotone map float -> uint32 (total order of finite floats, -0 < +0).
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---- the reference FPS tie rule --------------------------------------------------------------------------
+// The reference reduces per-thread candidates with a shared-memory tree that keeps the lower slot on ties
+// (sampling_gpu.cu:94-99,155-215) after a strided in-thread scan with strict '>' (:146-147).  The winner among
+// equal values is therefore the point k with the smallest bit-reversed slot (k mod B), then the smallest k / B,
+// with B = opt_n_threads(N) (cuda_utils.h:10-14).  prio(k) packs that order into 32 bits, smaller wins.
+__device__ __forceinline__ uint32_t fps_prio(uint32_t k, uint32_t log2B) {
+    uint32_t slot = k & ((1u << log2B) - 1u);
+    uint32_t rev = log2B ? (__brev(slot) >> (32 - log2B)) : 0u;
+    return (rev << 22) | (k >> log2B);
+}
+__device__ __forceinline__ uint32_t fps_prio_to_index(uint32_t prio, uint32_t log2B) {
+    uint32_t rev = prio >> 22;
+    uint32_t slot = log2B ? (__brev(rev) >> (32 - log2B)) : 0u;
+    return ((prio & 0x3FFFFFu) << log2B) | slot;
+}
+
+// Warp arg-max of (value-bits, priority) with two REDUX instructions.  `v` must be an order-preserving
+// uint32 image of the value; among equal v the smallest `prio` wins.  Returns the winning prio in `prio`.
+__device__ __forceinline__ void warp_argmax(uint32_t &v, uint32_t &prio) {
+    uint32_t vm = __reduce_max_sync(0xffffffffu, v);
+    uint32_t p = (v == vm) ? prio : 0xffffffffu;
+    prio = __reduce_min_sync(0xffffffffu, p);
+    v = vm;
+}
+
+}  // namespace de6d
+
+// Host-side error plumbing shared by all translation units (defined in capi.cu).
+extern "C" const char *de6d_last_error_string(void);
+int de6d_set_cuda_error(cudaError_t e, const char *where);
+int de6d_set_error(int code, const char *msg);
+
+void de6d_count_launch(void);
+
+#define DE6D_CHECK_LAUNCH(where)                                  \
+    do {                                                          \
+        cudaError_t e__ = cudaGetLastError();                     \
+        if (e__ != cudaSuccess) return de6d_set_cuda_error(e__, where); \
+        de6d_count_launch();                                      \
+    } while (0)

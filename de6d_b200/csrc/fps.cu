@@ -1,0 +1,557 @@
+// Farthest point sampling for sm_100a: D-FPS, S-FPS (semantics weighted) and F-FPS (distance matrix).
+//
+// Replaces pointnet2_batch/src/sampling_gpu.cu:101-585 of the reference (one strided CTA per cloud that
+// re-reads xyz and temp from global memory every iteration and reduces through a 10-level shared-memory
+// tree).  Results are bit-identical to that kernel, including its tie rule (common.cuh: fps_prio).
+//
+// Design (DESIGN.md section "FPS"):
+//   * one CTA per cloud, the whole cloud resident on chip: coordinates SoA in shared memory (192 KB for
+//     16384 points), running min-distances and tie priorities in registers;
+//   * points are Morton-sorted once per launch into buckets of 32 (one warp lane per point); every bucket
+//     keeps its bounding box, its largest min-distance and its cached arg-max.  A bucket whose box is
+//     farther from the newly selected point than its largest min-distance cannot change and is skipped.
+//     The lower bound is evaluated with the same rounded operations as the distance itself and every
+//     operation involved is monotone, so skipping is exact, not approximate (see bucket_lower_bound);
+//   * the per-iteration arg-max is REDUX (redux.sync) on order-preserving integer images of the floats:
+//     bucket -> warp -> CTA with ONE __syncthreads per selected point (double-buffered exchange slots).
+#include "common.cuh"
+#include <math.h>
+
+namespace de6d {
+
+enum { FPS_D = 0, FPS_S = 1 };
+
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ uint32_t part1by2(uint32_t x) {  // spread 10 bits to every third bit
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+// compact priority for clouds of at most 16384 points: (bit-reversed slot, k / B) in <= 14 bits
+__device__ __forceinline__ uint32_t cprio_of(uint32_t k, int log2B, int ibits) {
+    uint32_t slot = k & ((1u << log2B) - 1u);
+    uint32_t rev = log2B ? (__brev(slot) >> (32 - log2B)) : 0u;
+    return (rev << ibits) | (k >> log2B);
+}
+__device__ __forceinline__ uint32_t index_of_cprio(uint32_t cp, int log2B, int ibits) {
+    uint32_t rev = cp >> ibits;
+    uint32_t slot = log2B ? (__brev(rev) >> (32 - log2B)) : 0u;
+    return ((cp & ((1u << ibits) - 1u)) << log2B) | slot;
+}
+
+// S-FPS key: reference evaluates d * max(w, 1e-12) in double and rounds once to float
+// (sampling_gpu.cu:465; 1e-12 is a double literal).  For w >= 1e-12f the double product of two floats is
+// exact, so one float multiply gives the same rounding; only smaller weights take the double path.
+__device__ __forceinline__ float sfps_key(float d, float w) {
+    if (w >= 1e-11f) return __fmul_rn(d, w);
+    return (float)((double)d * fmax((double)w, 1e-12));
+}
+
+// Lower bound of sqdist(p, q) over every p inside the box: per axis the gap g = max(lo-q, q-hi, 0) satisfies
+// |fl(p-q)| >= g (rounding is monotone), and fl(dy*dy), fl(dx*dx+t), fl(dz*dz+t) are monotone in |d.| and t,
+// so the value below never exceeds the distance the kernel would compute for any point of the bucket.
+__device__ __forceinline__ float bucket_lower_bound(float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                                    float qx, float qy, float qz) {
+    float gx = fmaxf(fmaxf(__fsub_rn(lox, qx), __fsub_rn(qx, hix)), 0.f);
+    float gy = fmaxf(fmaxf(__fsub_rn(loy, qy), __fsub_rn(qy, hiy)), 0.f);
+    float gz = fmaxf(fmaxf(__fsub_rn(loz, qz), __fsub_rn(qz, hiz)), 0.f);
+    return __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+}
+
+template <int MODE, int NW, int BPW, bool PRUNE>
+__global__ void __launch_bounds__(NW * 32, 1)
+fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ xyz_all,
+                  const float *__restrict__ w_all, float *__restrict__ temp_all, int *__restrict__ idx_all) {
+    constexpr int T = NW * 32;
+    constexpr int CAP = NW * BPW * 32;
+    static_assert(BPW <= 32, "one owner lane per bucket");
+    if (m <= 0) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sx = reinterpret_cast<float *>(smem_raw);
+    float *sy = sx + CAP;
+    float *sz = sy + CAP;
+    uint2 *wbuf = reinterpret_cast<uint2 *>(sz + CAP);            // [2][NW]
+    float *red = reinterpret_cast<float *>(wbuf + 2 * NW);        // [6][NW] prologue reductions
+    int *misc = reinterpret_cast<int *>(red + 6 * NW);            // [0]=pos of index 0, [1]=non-finite flag
+    unsigned long long *sortbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // aliases sx/sy
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
+    const float *wts = MODE == FPS_S ? w_all + (size_t)blockIdx.x * n : nullptr;
+    float *temp_g = temp_all + (size_t)blockIdx.x * n;
+    int *idxs = idx_all + (size_t)blockIdx.x * m;
+
+    if (tid < 2) misc[tid] = 0;
+    __syncthreads();
+
+    // ---------------- prologue: order the cloud into buckets -----------------------------------------
+    uint32_t kk[BPW];  // original index of the point at (bucket j*NW+w, lane); 0xffffffff for padding
+    bool prune = PRUNE;
+    if (PRUNE) {
+        // cloud bounding box + finiteness
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        bool bad = false;
+        for (int k = tid; k < n; k += T) {
+            float t0 = temp_g[k];
+            bad |= (t0 != t0);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float v = xyz[k * 3 + a];
+                bad |= !(fabsf(v) <= 3.0e38f);
+                lo[a] = fminf(lo[a], v);
+                hi[a] = fmaxf(hi[a], v);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+            if (lane == 0) { red[a * NW + w] = lo[a]; red[(3 + a) * NW + w] = hi[a]; }
+        }
+        if (bad) misc[1] = 1;
+        __syncthreads();
+        float ext = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float l = INFINITY, h = -INFINITY;
+            for (int i = 0; i < NW; ++i) { l = fminf(l, red[a * NW + i]); h = fmaxf(h, red[(3 + a) * NW + i]); }
+            lo[a] = l;
+            ext = fmaxf(ext, h - l);
+        }
+        prune = (misc[1] == 0);
+        const float inv = ext > 0.f ? 1023.0f / ext : 0.f;
+        int np = 64;
+        while (np < n) np <<= 1;
+        __syncthreads();  // red[] fully consumed before sortbuf (aliasing only sx/sy, but keep phases apart)
+        for (int k = tid; k < np; k += T) {
+            unsigned long long item = ~0ull;
+            if (k < n) {
+                uint32_t key = 0;
+                if (prune) {
+                    uint32_t qx = (uint32_t)fminf(fmaxf((xyz[k * 3 + 0] - lo[0]) * inv, 0.f), 1023.f);
+                    uint32_t qy = (uint32_t)fminf(fmaxf((xyz[k * 3 + 1] - lo[1]) * inv, 0.f), 1023.f);
+                    uint32_t qz = (uint32_t)fminf(fmaxf((xyz[k * 3 + 2] - lo[2]) * inv, 0.f), 1023.f);
+                    key = part1by2(qx) | (part1by2(qy) << 1) | (part1by2(qz) << 2);
+                }
+                item = ((unsigned long long)key << 32) | (uint32_t)k;
+            }
+            sortbuf[k] = item;
+        }
+        __syncthreads();
+        for (unsigned kb = 2; kb <= (unsigned)np; kb <<= 1) {
+            for (unsigned jb = kb >> 1; jb > 0; jb >>= 1) {
+                for (unsigned i = tid; i < (unsigned)np / 2; i += T) {
+                    unsigned a = ((i & ~(jb - 1)) << 1) | (i & (jb - 1));
+                    unsigned b = a | jb;
+                    unsigned long long va = sortbuf[a], vb = sortbuf[b];
+                    bool up = (a & kb) == 0;
+                    if ((va > vb) == up) { sortbuf[a] = vb; sortbuf[b] = va; }
+                }
+                __syncthreads();
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < BPW; ++j) {
+            int p = ((j * NW + w) << 5) | lane;
+            kk[j] = p < n ? (uint32_t)sortbuf[p] : 0xffffffffu;
+        }
+        __syncthreads();  // every item read before the coordinates overwrite the sort buffer
+    } else {
+#pragma unroll
+        for (int j = 0; j < BPW; ++j) {
+            int p = ((j * NW + w) << 5) | lane;
+            kk[j] = p < n ? (uint32_t)p : 0xffffffffu;
+        }
+    }
+
+    // ---------------- load the cloud: coordinates -> smem, min-dist / priority / weight -> registers -------
+    float temp[BPW];
+    float wt[MODE == FPS_S ? BPW : 1];
+    uint32_t cpk[(BPW + 1) / 2];  // two 14-bit priorities per register
+#pragma unroll
+    for (int j = 0; j < (BPW + 1) / 2; ++j) cpk[j] = 0;
+    // per-lane bucket state (lane j owns bucket j*NW+w)
+    float blox = INFINITY, bhix = -INFINITY, bloy = INFINITY, bhiy = -INFINITY, bloz = INFINITY, bhiz = -INFINITY;
+    float bmaxt = -INFINITY;      // largest min-distance inside the bucket (pruning bound)
+    uint32_t bval = 0, bword = 0xffffffffu;  // cached arg-max of the bucket: ord(key) and (cprio<<14 | pos)
+
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+        const int p = ((j * NW + w) << 5) | lane;
+        const uint32_t k = kk[j];
+        float x = 0.f, y = 0.f, z = 0.f, t0 = -INFINITY;
+        uint32_t cp = 0x3fffu;
+        if (k != 0xffffffffu) {
+            x = xyz[k * 3 + 0]; y = xyz[k * 3 + 1]; z = xyz[k * 3 + 2];
+            t0 = temp_g[k];
+            cp = cprio_of(k, log2B, ibits);
+            if (MODE == FPS_S) wt[j] = wts[k];
+            if (k == 0) misc[0] = p;
+        } else if (MODE == FPS_S) {
+            wt[j] = 0.f;
+        }
+        sx[p] = x; sy[p] = y; sz[p] = z;
+        temp[j] = t0;
+        cpk[j >> 1] |= cp << (16 * (j & 1));
+        if (PRUNE) {
+            const bool valid = k != 0xffffffffu;
+            uint32_t a0 = __reduce_min_sync(0xffffffffu, valid ? f2ord(x) : 0xffffffffu);
+            uint32_t a1 = __reduce_max_sync(0xffffffffu, valid ? f2ord(x) : 0u);
+            uint32_t a2 = __reduce_min_sync(0xffffffffu, valid ? f2ord(y) : 0xffffffffu);
+            uint32_t a3 = __reduce_max_sync(0xffffffffu, valid ? f2ord(y) : 0u);
+            uint32_t a4 = __reduce_min_sync(0xffffffffu, valid ? f2ord(z) : 0xffffffffu);
+            uint32_t a5 = __reduce_max_sync(0xffffffffu, valid ? f2ord(z) : 0u);
+            uint32_t anyv = __ballot_sync(0xffffffffu, valid);
+            if (lane == j && anyv) {
+                blox = ord2f(a0); bhix = ord2f(a1); bloy = ord2f(a2); bhiy = ord2f(a3); bloz = ord2f(a4); bhiz = ord2f(a5);
+            }
+        }
+    }
+
+    // ---------------- first index -----------------------------------------------------------------------
+    // D-FPS starts from point 0 (sampling_gpu.cu:121-123); S-FPS from argmax(weights) with the same
+    // candidate rule (value must exceed -1) and tie order (:451-455).
+    int par = 0;
+    float x1, y1, z1;
+    int first_it;
+    __syncthreads();  // smem coordinates + misc[0] visible
+    if (MODE == FPS_D) {
+        const int p0 = misc[0];
+        x1 = sx[p0]; y1 = sy[p0]; z1 = sz[p0];
+        if (tid == 0) idxs[0] = 0;
+        first_it = 1;
+    } else {
+        uint32_t v = 0, wd = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < BPW; ++j) {
+            const int p = ((j * NW + w) << 5) | lane;
+            if (p < n) {
+                float val = wt[j];
+                uint32_t vv = (val == val) ? f2ord(val) : 0u;
+                uint32_t ww = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+                if (vv > v || (vv == v && ww < wd)) { v = vv; wd = ww; }
+            }
+        }
+        warp_argmax(v, wd);
+        if (lane == 0) wbuf[par * NW + w] = make_uint2(v, wd);
+        __syncthreads();
+        uint2 e = lane < NW ? wbuf[par * NW + lane] : make_uint2(0u, 0xffffffffu);
+        v = e.x; wd = e.y;
+        warp_argmax(v, wd);
+        par ^= 1;
+        int pos, k;
+        if (v != 0u && ord2f(v) > -1.0f) { pos = wd & 0x3fff; k = (int)index_of_cprio(wd >> 14, log2B, ibits); }
+        else { pos = misc[0]; k = 0; }
+        x1 = sx[pos]; y1 = sy[pos]; z1 = sz[pos];
+        if (tid == 0) idxs[0] = k;
+        first_it = 1;
+    }
+
+    // cached bucket arg-max from the caller's initial temp (normally 1e10 everywhere)
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+        const int p = ((j * NW + w) << 5) | lane;
+        float t = temp[j];
+        float val = MODE == FPS_S ? sfps_key(t, wt[j]) : t;
+        uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
+        uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+        uint32_t tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
+        warp_argmax(v, wd);
+        if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+    }
+
+    // ---------------- main loop: one selected point per iteration ------------------------------------------
+    for (int it = first_it; it < m; ++it) {
+        bool act = false;
+        if (lane < BPW) {
+            if (prune) {
+                float lb = bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, x1, y1, z1);
+                act = lb < bmaxt;
+            } else {
+                act = ((lane * NW + w) << 5) < n;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, act);
+#pragma unroll
+        for (int j = 0; j < BPW; ++j) {
+            if (mask & (1u << j)) {  // warp-uniform
+                const int p = ((j * NW + w) << 5) | lane;
+                float d = sqdist(sx[p], sy[p], sz[p], x1, y1, z1);
+                float t = fminf(d, temp[j]);
+                if (p >= n) t = -INFINITY;
+                temp[j] = t;
+                float val = MODE == FPS_S ? sfps_key(t, wt[j]) : t;
+                uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
+                uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+                uint32_t tm;
+                if (MODE == FPS_S) tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
+                warp_argmax(v, wd);
+                if (MODE == FPS_D) tm = v;
+                if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+            }
+        }
+        uint32_t v = bval, wd = bword;
+        warp_argmax(v, wd);
+        if (lane == 0) wbuf[par * NW + w] = make_uint2(v, wd);
+        __syncthreads();
+        uint2 e = lane < NW ? wbuf[par * NW + lane] : make_uint2(0u, 0xffffffffu);
+        par ^= 1;
+        v = e.x; wd = e.y;
+        warp_argmax(v, wd);
+        int pos, k;
+        if (v != 0u && ord2f(v) > -1.0f) { pos = wd & 0x3fff; k = (int)index_of_cprio(wd >> 14, log2B, ibits); }
+        else { pos = misc[0]; k = 0; }
+        x1 = sx[pos]; y1 = sy[pos]; z1 = sz[pos];
+        if (tid == 0) idxs[it] = k;
+    }
+
+    // ---------------- write the running min-distances back (temp is an in/out tensor of the op) ---------
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+        const int p = ((j * NW + w) << 5) | lane;
+        if (p < n) {
+            uint32_t cp = (cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            temp_g[index_of_cprio(cp, log2B, ibits)] = temp[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Generic any-N kernels (cloud does not fit on one SM): same arithmetic and tie rule, coordinates and
+// min-distances stay in global memory (L2 resident).  Also the F-FPS kernel, whose per-iteration input is
+// one matrix row (sampling_gpu.cu:268-373) -- no geometry, so no pruning; HBM/L2 latency bound.
+// ------------------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ uint32_t block_argmax_index(uint32_t v, uint32_t prio, uint2 *wbuf, int &par, uint32_t log2B) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int NW = T / 32;
+    warp_argmax(v, prio);
+    if (lane == 0) wbuf[par * NW + w] = make_uint2(v, prio);
+    __syncthreads();
+    uint2 e = lane < NW ? wbuf[par * NW + lane] : make_uint2(0u, 0xffffffffu);
+    par ^= 1;
+    v = e.x; prio = e.y;
+    warp_argmax(v, prio);
+    if (v != 0u && ord2f(v) > -1.0f) return fps_prio_to_index(prio, log2B);
+    return 0u;
+}
+
+template <int MODE, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_global_kernel(int n, int m, int log2B, const float *__restrict__ xyz_all, const float *__restrict__ w_all,
+                  float *__restrict__ temp_all, int *__restrict__ idx_all) {
+    if (m <= 0) return;
+    __shared__ uint2 wbuf[2 * (T / 32)];
+    const int tid = threadIdx.x;
+    const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
+    const float *wts = MODE == FPS_S ? w_all + (size_t)blockIdx.x * n : nullptr;
+    float *temp = temp_all + (size_t)blockIdx.x * n;
+    int *idxs = idx_all + (size_t)blockIdx.x * m;
+    int par = 0, old = 0, first_it = 1;
+    if (MODE == FPS_S) {
+        uint32_t bv = 0, bp = 0xffffffffu;
+        for (int k = tid; k < n; k += T) {
+            float val = wts[k];
+            uint32_t v = (val == val) ? f2ord(val) : 0u, pr = fps_prio(k, log2B);
+            if (v > bv || (v == bv && pr < bp)) { bv = v; bp = pr; }
+        }
+        old = (int)block_argmax_index<T>(bv, bp, wbuf, par, log2B);
+    }
+    if (tid == 0) idxs[0] = old;
+    for (int it = first_it; it < m; ++it) {
+        const float x1 = xyz[old * 3 + 0], y1 = xyz[old * 3 + 1], z1 = xyz[old * 3 + 2];
+        uint32_t bv = 0, bp = 0xffffffffu;
+        for (int k = tid; k < n; k += T) {
+            float d = sqdist(xyz[k * 3 + 0], xyz[k * 3 + 1], xyz[k * 3 + 2], x1, y1, z1);
+            float t = fminf(d, temp[k]);
+            temp[k] = t;
+            float val = MODE == FPS_S ? sfps_key(t, wts[k]) : t;
+            uint32_t v = (val == val) ? f2ord(val) : 0u, pr = fps_prio(k, log2B);
+            if (v > bv || (v == bv && pr < bp)) { bv = v; bp = pr; }
+        }
+        old = (int)block_argmax_index<T>(bv, bp, wbuf, par, log2B);
+        if (tid == 0) idxs[it] = old;
+    }
+}
+
+// F-FPS.  Thread t owns columns 4*(t + c*T) .. +3 for chunk c < NCH: the running min-distances of those
+// columns stay in registers when REG (n <= 4*T*NCH), one 128-bit load per chunk fetches the matrix row.
+template <int T, int NCH, bool REG, bool VEC>
+__global__ void __launch_bounds__(T, 1)
+fps_matrix_kernel(int n, int m, int log2B, const float *__restrict__ mat_all, float *__restrict__ temp_all,
+                  int *__restrict__ idx_all) {
+    if (m <= 0) return;
+    __shared__ uint2 wbuf[2 * (T / 32)];
+    const int tid = threadIdx.x;
+    const float *mat = mat_all + (size_t)blockIdx.x * n * n;
+    float *temp_g = temp_all + (size_t)blockIdx.x * n;
+    int *idxs = idx_all + (size_t)blockIdx.x * m;
+    float tr[REG ? NCH * 4 : 1];
+    if (REG) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int k = 4 * (tid + c * T) + q;
+                tr[c * 4 + q] = k < n ? temp_g[k] : -INFINITY;
+            }
+    }
+    int par = 0, old = 0;
+    if (tid == 0) idxs[0] = 0;
+    for (int it = 1; it < m; ++it) {
+        const float *row = mat + (size_t)old * n;
+        uint32_t bv = 0, bp = 0xffffffffu;
+        if (REG) {
+            float dv[NCH * 4];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                int k0 = 4 * (tid + c * T);
+                if (VEC) {
+                    float4 r = k0 < n ? __ldg(reinterpret_cast<const float4 *>(row + k0)) : make_float4(0, 0, 0, 0);
+                    dv[c * 4 + 0] = r.x; dv[c * 4 + 1] = r.y; dv[c * 4 + 2] = r.z; dv[c * 4 + 3] = r.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dv[c * 4 + q] = (k0 + q) < n ? __ldg(row + k0 + q) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int k = 4 * (tid + c * T) + q;
+                    if (k < n) {
+                        float t = fminf(dv[c * 4 + q], tr[c * 4 + q]);
+                        tr[c * 4 + q] = t;
+                        uint32_t v = (t == t) ? f2ord(t) : 0u, pr = fps_prio(k, log2B);
+                        if (v > bv || (v == bv && pr < bp)) { bv = v; bp = pr; }
+                    }
+                }
+        } else {
+            for (int k = tid; k < n; k += T) {
+                float t = fminf(__ldg(row + k), temp_g[k]);
+                temp_g[k] = t;
+                uint32_t v = (t == t) ? f2ord(t) : 0u, pr = fps_prio(k, log2B);
+                if (v > bv || (v == bv && pr < bp)) { bv = v; bp = pr; }
+            }
+        }
+        old = (int)block_argmax_index<T>(bv, bp, wbuf, par, log2B);
+        if (tid == 0) idxs[it] = old;
+    }
+    if (REG) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int k = 4 * (tid + c * T) + q;
+                if (k < n) temp_g[k] = tr[c * 4 + q];
+            }
+    }
+}
+
+// ---------------------------------- host side ----------------------------------------------------------
+static int ref_log2_block(int n) {  // opt_n_threads (cuda_utils.h:10-14), same double arithmetic
+    int p = (int)(log((double)n) / log(2.0));
+    int v = 1 << p;
+    if (v > 1024) { v = 1024; p = 10; }
+    if (v < 1) { v = 1; p = 0; }
+    return p;
+}
+
+template <int MODE, int NW, int BPW, bool PRUNE>
+static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float *xyz, const float *w, float *temp,
+                         int *idx, cudaStream_t s) {
+    constexpr int CAP = NW * BPW * 32;
+    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16;
+    static bool configured = false;  // attribute is per-function, set once per process (idempotent, race-benign)
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<MODE, NW, BPW, PRUNE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return de6d_set_cuda_error(e, "fps smem attribute");
+        configured = true;
+    }
+    fps_bucket_kernel<MODE, NW, BPW, PRUNE><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
+    DE6D_CHECK_LAUNCH("fps_bucket_kernel");
+    return DE6D_OK;
+}
+
+template <int MODE>
+static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, float *temp, int *idx, int impl,
+                        cudaStream_t s) {
+    if (b < 0 || n < 0 || m < 0) return de6d_set_error(DE6D_ERR_INVALID, "fps: negative size");
+    if (b == 0 || m == 0) return DE6D_OK;
+    if (n == 0) return de6d_set_error(DE6D_ERR_INVALID, "fps: empty cloud with npoint > 0");
+    if (!xyz || !temp || !idx || (MODE == FPS_S && !w)) return de6d_set_error(DE6D_ERR_INVALID, "fps: null pointer");
+    const int log2B = ref_log2_block(n);
+    int ibits = 0;
+    while (((n - 1) >> log2B) >> ibits) ++ibits;
+    const bool prune = impl != 1;
+    if (n <= 16384 && impl != 2 && log2B + ibits <= 14) {
+        if (n <= 1024)
+            return prune ? launch_bucket<MODE, 8, 4, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s)
+                         : launch_bucket<MODE, 8, 4, false>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+        if (n <= 4096)
+            return prune ? launch_bucket<MODE, 16, 8, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s)
+                         : launch_bucket<MODE, 16, 8, false>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+        return prune ? launch_bucket<MODE, 16, 32, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s)
+                     : launch_bucket<MODE, 16, 32, false>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+    }
+    fps_global_kernel<MODE, 1024><<<b, 1024, 0, s>>>(n, m, log2B, xyz, w, temp, idx);
+    DE6D_CHECK_LAUNCH("fps_global_kernel");
+    return DE6D_OK;
+}
+
+}  // namespace de6d
+
+using namespace de6d;
+
+// impl: 0 = default (bucket-pruned on-chip kernel when the cloud fits, else generic), 1 = on-chip kernel without
+// pruning (every bucket visited every iteration), 2 = generic global-memory kernel.  All give identical results.
+extern "C" int de6d_furthest_point_sampling_impl(int b, int n, int m, const float *xyz, float *temp, int *idx, int impl,
+                                                 cudaStream_t stream) {
+    return fps_dispatch<FPS_D>(b, n, m, xyz, nullptr, temp, idx, impl, stream);
+}
+extern "C" int de6d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                            cudaStream_t stream) {
+    return fps_dispatch<FPS_D>(b, n, m, xyz, nullptr, temp, idx, 0, stream);
+}
+extern "C" int de6d_furthest_point_sampling_weights_impl(int b, int n, int m, const float *xyz, const float *weights,
+                                                         float *temp, int *idx, int impl, cudaStream_t stream) {
+    return fps_dispatch<FPS_S>(b, n, m, xyz, weights, temp, idx, impl, stream);
+}
+extern "C" int de6d_furthest_point_sampling_weights(int b, int n, int m, const float *xyz, const float *weights,
+                                                    float *temp, int *idx, cudaStream_t stream) {
+    return fps_dispatch<FPS_S>(b, n, m, xyz, weights, temp, idx, 0, stream);
+}
+
+extern "C" int de6d_furthest_point_sampling_matrix(int b, int n, int m, const float *matrix, float *temp, int *idx,
+                                                   cudaStream_t stream) {
+    if (b < 0 || n < 0 || m < 0) return de6d_set_error(DE6D_ERR_INVALID, "fps_matrix: negative size");
+    if (b == 0 || m == 0) return DE6D_OK;
+    if (n == 0) return de6d_set_error(DE6D_ERR_INVALID, "fps_matrix: empty cloud with npoint > 0");
+    if (!matrix || !temp || !idx) return de6d_set_error(DE6D_ERR_INVALID, "fps_matrix: null pointer");
+    const int log2B = ref_log2_block(n);
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(matrix) & 15) == 0);
+    constexpr int T = 1024;
+    if (n <= 4 * T) {
+        if (vec) fps_matrix_kernel<T, 1, true, true><<<b, T, 0, stream>>>(n, m, log2B, matrix, temp, idx);
+        else fps_matrix_kernel<T, 1, true, false><<<b, T, 0, stream>>>(n, m, log2B, matrix, temp, idx);
+    } else if (n <= 16 * T) {
+        if (vec) fps_matrix_kernel<T, 4, true, true><<<b, T, 0, stream>>>(n, m, log2B, matrix, temp, idx);
+        else fps_matrix_kernel<T, 4, true, false><<<b, T, 0, stream>>>(n, m, log2B, matrix, temp, idx);
+    } else {
+        fps_matrix_kernel<T, 1, false, false><<<b, T, 0, stream>>>(n, m, log2B, matrix, temp, idx);
+    }
+    DE6D_CHECK_LAUNCH("fps_matrix_kernel");
+    return DE6D_OK;
+}

@@ -1,0 +1,252 @@
+// group_points / gather_points (+ their gradients) for sm_100a.
+//
+// Replaces pointnet2_batch/src/group_points_gpu.cu:14-72 and sampling_gpu.cu:16-71 (one thread per output
+// element, the index tensor re-read once per channel, 4-byte stores).  Pure copies, so bit-exact by
+// construction; the work is moving bytes:
+//   out[b, c, j] = points[b, c, idx[b, j]],   j over npoints*nsample (gather_points is the nsample = 1 case)
+//
+// Two kernels, picked per call by the host:
+//   * staged: a CTA stages G whole channel rows of one cloud (G*N*4 bytes, up to ~192 KB) in shared memory
+//     with one TMA bulk copy per row (cp.async.bulk + mbarrier), then streams its slice of the index tensor
+//     once (128-bit loads) and emits G output rows with 128-bit stores.  Random 4-byte reads hit shared
+//     memory instead of 32-byte L2 sectors, and idx is read once per G channels instead of once per channel.
+//   * direct: few outputs per source row (e.g. gathering 4096 of 16384 points) or rows too large for shared
+//     memory -- 128-bit index loads, read-only-path gathers, 128-bit stores, channel loop inside the thread.
+#include "common.cuh"
+
+namespace de6d {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// 1-D TMA bulk copy global -> shared (SASS: UBLKCP); bytes and both addresses must be multiples of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ int4 ldg_stream_int4(const int *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_float4(float *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr int GS_THREADS = 512;
+
+// grid: (chunks, ceil(C/G), B).  Dynamic smem: G*n_pad floats + one mbarrier.
+template <bool TMA>
+__global__ void __launch_bounds__(GS_THREADS)
+group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chunk, const float *__restrict__ points,
+                    const int *__restrict__ idx, float *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float *rows = reinterpret_cast<float *>(smem_raw + 128);
+
+    const int bs = blockIdx.z;
+    const int c0 = blockIdx.y * G;
+    const int g_here = min(G, c - c0);
+    const float *src = points + ((size_t)bs * c + c0) * n;
+
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (uint32_t)g_here * (uint32_t)n * 4u);
+            for (int g = 0; g < g_here; ++g) tma_bulk_g2s(rows + (size_t)g * n_pad, src + (size_t)g * n, (uint32_t)n * 4u, bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        for (int g = 0; g < g_here; ++g)
+            for (int i = threadIdx.x; i < n; i += GS_THREADS) rows[(size_t)g * n_pad + i] = src[(size_t)g * n + i];
+        __syncthreads();
+    }
+
+    const long long j0 = (long long)blockIdx.x * chunk;
+    const long long j1 = min(ms, j0 + chunk);
+    const int *ix = idx + (size_t)bs * ms;
+    float *dst = out + ((size_t)bs * c + c0) * ms;
+    // chunk is a multiple of 4 and ms % 4 == 0 is checked by the host for this kernel
+    for (long long j = j0 + 4ll * threadIdx.x; j < j1; j += 4ll * GS_THREADS) {
+        const int4 k = ldg_stream_int4(ix + j);
+        for (int g = 0; g < g_here; ++g) {
+            const float *r = rows + (size_t)g * n_pad;
+            float4 v = make_float4(r[k.x], r[k.y], r[k.z], r[k.w]);
+            stg_stream_float4(dst + (size_t)g * ms + j, v);
+        }
+    }
+}
+
+// direct gathers; CPT channels per thread (idx held in registers across them).  grid: (x, ceil(C/CPT), B)
+template <int CPT>
+__global__ void __launch_bounds__(256)
+group_direct_kernel(int c, int n, long long ms, int vec, const float *__restrict__ points, const int *__restrict__ idx,
+                    float *__restrict__ out) {
+    const int bs = blockIdx.z;
+    const int c0 = blockIdx.y * CPT;
+    const int *ix = idx + (size_t)bs * ms;
+    const float *src = points + ((size_t)bs * c + c0) * n;
+    float *dst = out + ((size_t)bs * c + c0) * ms;
+    const int ch = min(CPT, c - c0);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (vec) {
+        for (long long j4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; j4 * 4 < ms; j4 += stride) {
+            const long long j = j4 * 4;
+            const int4 k = *reinterpret_cast<const int4 *>(ix + j);
+#pragma unroll
+            for (int g = 0; g < CPT; ++g) {
+                if (g < ch) {
+                    const float *r = src + (size_t)g * n;
+                    float4 v = make_float4(__ldg(r + k.x), __ldg(r + k.y), __ldg(r + k.z), __ldg(r + k.w));
+                    *reinterpret_cast<float4 *>(dst + (size_t)g * ms + j) = v;
+                }
+            }
+        }
+    } else {
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ms; j += stride) {
+            const int k = ix[j];
+#pragma unroll
+            for (int g = 0; g < CPT; ++g)
+                if (g < ch) dst[(size_t)g * ms + j] = __ldg(src + (size_t)g * n + k);
+        }
+    }
+}
+
+// gradient: grad_points[b, c, idx[b, j]] += grad_out[b, c, j]   (group_points_gpu.cu:14-31, sampling_gpu.cu:54-71)
+template <int CPT>
+__global__ void __launch_bounds__(256)
+group_grad_kernel(int c, int n, long long ms, const float *__restrict__ grad_out, const int *__restrict__ idx,
+                  float *__restrict__ grad_points) {
+    const int bs = blockIdx.z;
+    const int c0 = blockIdx.y * CPT;
+    const int ch = min(CPT, c - c0);
+    const int *ix = idx + (size_t)bs * ms;
+    const float *g_out = grad_out + ((size_t)bs * c + c0) * ms;
+    float *g_pts = grad_points + ((size_t)bs * c + c0) * n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ms; j += stride) {
+        const int k = ix[j];
+#pragma unroll
+        for (int g = 0; g < CPT; ++g)
+            if (g < ch) atomicAdd(g_pts + (size_t)g * n + k, g_out[(size_t)g * ms + j]);
+    }
+}
+
+static int group_forward(int b, int c, int n, long long ms, const float *points, const int *idx, float *out,
+                         int force_impl, cudaStream_t s) {
+    if (b < 0 || c < 0 || n < 0 || ms < 0) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: negative size");
+    if (b == 0 || c == 0 || ms == 0) return DE6D_OK;
+    if (!points || !idx || !out) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: null pointer");
+    if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: batch > 65535");
+
+    // staged kernel: rows must fit, outputs per row must amortise the staging, 16-byte alignment everywhere
+    const size_t smem_budget = 200 * 1024;
+    const int n_pad = (n + 3) & ~3;
+    const bool aligned = (ms % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool tma_ok = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    int G = (int)(smem_budget / ((size_t)n_pad * 4 + 1));
+    if (G > c) G = c;
+    if (G > 16) G = 16;
+    bool staged = aligned && G >= 1 && ms >= 2ll * n;
+    if (force_impl == 1) staged = false;
+    if (force_impl == 2 && !(aligned && G >= 1)) return de6d_set_error(DE6D_ERR_INVALID, "group: staged kernel not applicable");
+    if (force_impl == 2) staged = true;
+
+    if (staged) {
+        const int cgroups = ceil_div(c, G);
+        // enough CTAs to fill the machine, but each CTA should write >= ~2x what it stages
+        long long min_chunk = (long long)n * 2;
+        if (min_chunk < 4096) min_chunk = 4096;
+        long long want = ceil_div_ll(2 * 148, (long long)b * cgroups);
+        long long chunks = want < 1 ? 1 : want;
+        long long chunk = ceil_div_ll(ms, chunks);
+        if (chunk < min_chunk) chunk = min_chunk;
+        chunk = (chunk + 3) & ~3ll;
+        chunks = ceil_div_ll(ms, chunk);
+        size_t smem = 128 + (size_t)G * n_pad * 4;
+        static size_t configured[2] = {0, 0};
+        const int t = tma_ok ? 1 : 0;
+        if (smem > 48 * 1024 && configured[t] == 0) {
+            cudaError_t e = tma_ok ? cudaFuncSetAttribute(group_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)
+                                   : cudaFuncSetAttribute(group_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+            if (e != cudaSuccess) return de6d_set_cuda_error(e, "group smem attribute");
+            configured[t] = 1;
+        }
+        dim3 grid((unsigned)chunks, cgroups, b);
+        if (tma_ok) group_staged_kernel<true><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out);
+        else group_staged_kernel<false><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out);
+        DE6D_CHECK_LAUNCH("group_staged_kernel");
+        return DE6D_OK;
+    }
+    constexpr int CPT = 4;
+    const int vec = aligned ? 1 : 0;
+    long long work = vec ? ms / 4 : ms;
+    long long bx = ceil_div_ll(work, 256);
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, ceil_div(c, CPT), b);
+    group_direct_kernel<CPT><<<grid, 256, 0, s>>>(c, n, ms, vec, points, idx, out);
+    DE6D_CHECK_LAUNCH("group_direct_kernel");
+    return DE6D_OK;
+}
+
+static int group_backward(int b, int c, int n, long long ms, const float *grad_out, const int *idx, float *grad_points,
+                          cudaStream_t s) {
+    if (b < 0 || c < 0 || n < 0 || ms < 0) return de6d_set_error(DE6D_ERR_INVALID, "group/gather grad: negative size");
+    if (b == 0 || c == 0 || ms == 0) return DE6D_OK;
+    if (!grad_out || !idx || !grad_points) return de6d_set_error(DE6D_ERR_INVALID, "group/gather grad: null pointer");
+    if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "group/gather grad: batch > 65535");
+    constexpr int CPT = 4;
+    long long bx = ceil_div_ll(ms, 256);
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, ceil_div(c, CPT), b);
+    group_grad_kernel<CPT><<<grid, 256, 0, s>>>(c, n, ms, grad_out, idx, grad_points);
+    DE6D_CHECK_LAUNCH("group_grad_kernel");
+    return DE6D_OK;
+}
+
+}  // namespace de6d
+
+using namespace de6d;
+
+extern "C" int de6d_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                                 float *out, cudaStream_t stream) {
+    return group_forward(b, c, n, (long long)npoints * nsample, points, idx, out, 0, stream);
+}
+// impl: 0 auto, 1 direct-gather kernel, 2 shared-memory staged (TMA) kernel -- identical results
+extern "C" int de6d_group_points_impl(int b, int c, int n, int npoints, int nsample, const float *points,
+                                      const int *idx, float *out, int impl, cudaStream_t stream) {
+    return group_forward(b, c, n, (long long)npoints * nsample, points, idx, out, impl, stream);
+}
+extern "C" int de6d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                                      const int *idx, float *grad_points, cudaStream_t stream) {
+    return group_backward(b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points, stream);
+}
+extern "C" int de6d_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                                  cudaStream_t stream) {
+    return group_forward(b, c, n, (long long)npoints, points, idx, out, 0, stream);
+}
+extern "C" int de6d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                                       float *grad_points, cudaStream_t stream) {
+    return group_backward(b, c, n, (long long)npoints, grad_out, idx, grad_points, stream);
+}

@@ -1,0 +1,107 @@
+"""Host-side mirror of pcdet/ops/iou3d_nms/iou3d_nms_utils.py: same names and return values, B200 kernels
+underneath.  Additions (not in the reference): `nms_gpu_batched` -- the sync-free batched form used by the
+op chain -- and the fused single-kernel `boxes_iou3d_gpu`.
+"""
+import numpy as np
+import torch
+
+from ._lib import call, load
+from .compat import iou3d_nms_cuda as _ext
+
+
+def _to_torch(x):
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(x).float(), True
+    return x, False
+
+
+def boxes_bev_iou_cpu(boxes_a, boxes_b):
+    """(reference :12-28) CPU tensors / numpy in, same kind out; computed on the device."""
+    boxes_a, is_numpy = _to_torch(boxes_a)
+    boxes_b, _ = _to_torch(boxes_b)
+    assert not (boxes_a.is_cuda or boxes_b.is_cuda), 'Only support CPU tensors'
+    assert boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7
+    ans_iou = boxes_a.new_zeros(torch.Size((boxes_a.shape[0], boxes_b.shape[0])))
+    _ext.boxes_iou_bev_cpu(boxes_a.contiguous(), boxes_b.contiguous(), ans_iou)
+    return ans_iou.numpy() if is_numpy else ans_iou
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    """(reference :31-45) rotated BEV IoU, (N, 7) x (M, 7) -> (N, M)."""
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    ans_iou = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    _ext.boxes_iou_bev_gpu(boxes_a.contiguous(), boxes_b.contiguous(), ans_iou)
+    return ans_iou
+
+
+def boxes_iou3d_gpu(boxes_a, boxes_b):
+    """(reference :48-81) 3-D IoU = BEV overlap x height overlap / union volume, one fused kernel that rounds
+    after every step exactly where the reference's separate torch kernels do."""
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    ans = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    _ext.boxes_iou3d_gpu(boxes_a.contiguous(), boxes_b.contiguous(), ans)
+    return ans
+
+
+def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
+    """(reference :84-99) returns (indices into `boxes` of the kept boxes in descending score order, None)."""
+    assert boxes.shape[1] == 7
+    order = scores.sort(0, descending=True)[1]
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    boxes = boxes[order].contiguous()
+    keep = torch.empty(boxes.size(0), dtype=torch.int64)
+    num_out = _ext.nms_gpu(boxes, keep, thresh)
+    return order[keep[:num_out].to(boxes.device)].contiguous(), None
+
+
+def nms_normal_gpu(boxes, scores, thresh, **kwargs):
+    """(reference :102-116) axis-aligned variant."""
+    assert boxes.shape[1] == 7
+    order = scores.sort(0, descending=True)[1]
+    boxes = boxes[order].contiguous()
+    keep = torch.empty(boxes.size(0), dtype=torch.int64)
+    num_out = _ext.nms_normal_gpu(boxes, keep, thresh)
+    return order[keep[:num_out].to(boxes.device)].contiguous(), None
+
+
+class BatchedNMS:
+    """Sync-free NMS over a whole batch of frames: one sort, one gather, one kernel launch; outputs stay on the
+    device as padded tensors.  Equivalent to calling `nms_gpu` frame by frame (detector3d_template.py:199-282
+    does that in a Python loop with a malloc + D2H + host sweep + H2D per frame).
+
+        nms = BatchedNMS(frames, n)                      # owns the workspace, reusable / graph-capturable
+        keep, num = nms(boxes, scores, thresh)           # keep (F, n) int64 indices into boxes[f], num (F) int32
+    """
+
+    def __init__(self, frames, n, device="cuda"):
+        self.frames, self.n = frames, n
+        lib = load()
+        self.ws_bytes = int(lib.de6d_nms_workspace_bytes(frames, n))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        call("de6d_nms_workspace_init", frames, self.ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        self.keep_pos = torch.zeros((frames, n), dtype=torch.int64, device=device)
+        self.num = torch.zeros(frames, dtype=torch.int32, device=device)
+
+    def __call__(self, boxes, scores, thresh, nvalid=None, normal=False, presorted=False):
+        F, n = self.frames, self.n
+        assert boxes.shape == (F, n, 7) and boxes.dtype == torch.float32
+        if presorted:
+            order, sorted_boxes = None, boxes.contiguous()
+        else:
+            order = scores.sort(1, descending=True)[1]
+            sorted_boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, 7)).contiguous()
+        call("de6d_nms_batched", F, n, sorted_boxes.data_ptr(), None if nvalid is None else nvalid.data_ptr(),
+             float(thresh), int(bool(normal)), self.keep_pos.data_ptr(), self.num.data_ptr(), self.ws.data_ptr(),
+             self.ws_bytes, torch.cuda.current_stream().cuda_stream)
+        if order is None:
+            return self.keep_pos, self.num
+        # positions -> original indices; entries beyond num[f] are padding (position 0)
+        return torch.gather(order, 1, self.keep_pos), self.num
+
+
+def nms_gpu_batched(boxes, scores, thresh, nvalid=None, normal=False):
+    """Functional form of BatchedNMS for one-off calls: boxes (F, n, 7), scores (F, n)."""
+    op = BatchedNMS(boxes.shape[0], boxes.shape[1], device=boxes.device)
+    keep, num = op(boxes, scores, thresh, nvalid=nvalid, normal=normal)
+    return keep.clone(), num.clone()

@@ -1,0 +1,288 @@
+"""Host-side mirror of the reference op wrappers pcdet/ops/pointnet2/pointnet2_batch/pointnet2_utils.py:
+the same public names, argument meaning and return values, on top of de6d_b200.compat.pointnet2_batch_cuda
+(hand-written sm_100a kernels behind the C ABI).  Output/scratch tensors are allocated here with the same
+pre-initialisation the reference relies on (temp = 1e10, idx = 0, idx_cnt = 0, grads = 0).
+"""
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from .compat import pointnet2_batch_cuda as _ext
+
+
+def _new(ref: torch.Tensor, shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=ref.device)
+
+
+class FarthestPointSampling(Function):
+    """D-FPS (reference :10-33).  xyz (B, N, 3) -> (B, npoint) int32; index 0 is always selected first."""
+
+    @staticmethod
+    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+        assert xyz.is_contiguous()
+        B, N, _ = xyz.size()
+        out = _new(xyz, (B, npoint), torch.int32)
+        temp = _new(xyz, (B, N), torch.float32).fill_(1e10)
+        _ext.farthest_point_sampling_wrapper(B, N, npoint, xyz, temp, out)
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+farthest_point_sample = furthest_point_sample = FarthestPointSampling.apply
+
+
+@torch.no_grad()
+def calc_dist_matrix_for_sampling(xyz: torch.Tensor, features: torch.Tensor = None, gamma: float = 1.0):
+    """F-FPS input (reference :36-44): pairwise L2 of coordinates plus gamma * pairwise L2 of features."""
+    dist = torch.cdist(xyz, xyz)
+    if features is not None:
+        dist += torch.cdist(features, features) * gamma
+    return dist
+
+
+@torch.no_grad()
+def furthest_point_sample_matrix(matrix: torch.Tensor, npoint: int) -> torch.Tensor:
+    """F-FPS on a (B, N, N) distance matrix (reference :69-86)."""
+    assert matrix.is_contiguous()
+    B, N, _ = matrix.size()
+    out = _new(matrix, (B, npoint), torch.int32)
+    temp = _new(matrix, (B, N), torch.float32).fill_(1e10)
+    _ext.furthest_point_sampling_matrix_wrapper(B, N, npoint, matrix, temp, out)
+    return out
+
+
+@torch.no_grad()
+def furthest_point_sample_weights(xyz: torch.Tensor, weights: torch.Tensor, npoint: int) -> torch.Tensor:
+    """S-FPS (reference :89-109): first pick = argmax(weights), then argmax of min-dist * max(w, 1e-12)."""
+    assert xyz.is_contiguous()
+    assert weights.is_contiguous()
+    B, N, _ = xyz.size()
+    out = _new(xyz, (B, npoint), torch.int32)
+    temp = _new(xyz, (B, N), torch.float32).fill_(1e10)
+    _ext.furthest_point_sampling_weights_wrapper(B, N, npoint, xyz, weights, temp, out)
+    return out
+
+
+class GatherOperation(Function):
+    """features (B, C, N), idx (B, npoint) -> (B, C, npoint) (reference :115-146)."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        B, npoint = idx.size()
+        _, C, N = features.size()
+        out = _new(features, (B, C, npoint), torch.float32)
+        _ext.gather_points_wrapper(B, C, N, npoint, features, idx, out)
+        ctx.for_backwards = (idx, C, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, C, N = ctx.for_backwards
+        B, npoint = idx.size()
+        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
+        _ext.gather_points_grad_wrapper(B, C, N, npoint, grad_out.detach().contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+gather_operation = GatherOperation.apply
+
+
+class ThreeNN(Function):
+    """unknown (B, N, 3), known (B, M, 3) -> (sqrt of the 3 smallest squared distances, their indices)
+    (reference :152-178)."""
+
+    @staticmethod
+    def forward(ctx, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        assert unknown.is_contiguous()
+        assert known.is_contiguous()
+        B, N, _ = unknown.size()
+        m = known.size(1)
+        dist2 = _new(unknown, (B, N, 3), torch.float32)
+        idx = _new(unknown, (B, N, 3), torch.int32)
+        _ext.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
+        dist = torch.sqrt(dist2)
+        ctx.mark_non_differentiable(dist, idx)
+        return dist, idx
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None
+
+
+three_nn = ThreeNN.apply
+
+
+class ThreeInterpolate(Function):
+    """features (B, C, M), idx/weight (B, n, 3) -> (B, C, n) (reference :184-226)."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        assert weight.is_contiguous()
+        B, c, m = features.size()
+        n = idx.size(1)
+        ctx.three_interpolate_for_backward = (idx, weight, m)
+        out = _new(features, (B, c, n), torch.float32)
+        _ext.three_interpolate_wrapper(B, c, m, n, features, idx, weight, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        idx, weight, m = ctx.three_interpolate_for_backward
+        B, c, n = grad_out.size()
+        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
+        _ext.three_interpolate_grad_wrapper(B, c, n, m, grad_out.detach().contiguous(), idx, weight, grad_features)
+        return grad_features, None, None
+
+
+three_interpolate = ThreeInterpolate.apply
+
+
+class GroupingOperation(Function):
+    """features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample) (reference :232-270)."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        assert features.is_contiguous()
+        assert idx.is_contiguous()
+        B, nfeatures, nsample = idx.size()
+        _, C, N = features.size()
+        out = _new(features, (B, C, nfeatures, nsample), torch.float32)
+        _ext.group_points_wrapper(B, C, N, nfeatures, nsample, features, idx, out)
+        ctx.for_backwards = (idx, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        idx, N = ctx.for_backwards
+        B, C, npoint, nsample = grad_out.size()
+        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
+        _ext.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.detach().contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+grouping_operation = GroupingOperation.apply
+
+
+class BallQuery(Function):
+    """(reference :276-301) first `nsample` neighbours (ascending index) within `radius`, padded with the first."""
+
+    @staticmethod
+    def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+        assert new_xyz.is_contiguous()
+        assert xyz.is_contiguous()
+        B, N, _ = xyz.size()
+        npoint = new_xyz.size(1)
+        idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        _ext.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+ball_query = BallQuery.apply
+
+
+@torch.no_grad()
+def ball_query_cnt(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor):
+    """(reference :307-327) -> (idx_cnt (B, npoint), idx (B, npoint, nsample)); hit list repeated cyclically."""
+    assert new_xyz.is_contiguous()
+    assert xyz.is_contiguous()
+    B, N, _ = xyz.size()
+    npoint = new_xyz.size(1)
+    idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+    idx_cnt = torch.zeros((B, npoint), dtype=torch.int32, device=xyz.device)
+    _ext.ball_query_cnt_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx_cnt, idx)
+    return idx_cnt, idx
+
+
+@torch.no_grad()
+def ball_query_dilated(radius_in: float, radius_out: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor):
+    """(reference :330-351) shell radius_in <= d < radius_out."""
+    assert new_xyz.is_contiguous()
+    assert xyz.is_contiguous()
+    B, N, _ = xyz.size()
+    npoint = new_xyz.size(1)
+    idx_cnt = torch.zeros((B, npoint), dtype=torch.int32, device=xyz.device)
+    idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+    _ext.ball_query_dilated_wrapper(B, N, npoint, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx)
+    return idx_cnt, idx
+
+
+def _assemble(xyz, new_xyz, features, idx, use_xyz):
+    """Shared tail of the three grouper modules (reference :368-387, :410-424, :449-463)."""
+    xyz_trans = xyz.transpose(1, 2).contiguous()
+    grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
+    grouped_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
+    if features is not None:
+        grouped_features = grouping_operation(features, idx)
+        if use_xyz:
+            return torch.cat([grouped_xyz, grouped_features], dim=1)  # (B, 3 + C, npoint, nsample)
+        return grouped_features
+    assert use_xyz, "Cannot have not features and not use xyz as a feature!"
+    return grouped_xyz
+
+
+class QueryAndGroup(nn.Module):
+    """(reference :354-387)"""
+
+    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        return _assemble(xyz, new_xyz, features, idx, self.use_xyz)
+
+
+class QueryWithCntAndGroup(nn.Module):
+    """(reference :390-424) -- the grouper Det6D / SASA use."""
+
+    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        idx_cnt, idx = ball_query_cnt(self.radius, self.nsample, xyz, new_xyz)
+        return idx_cnt, _assemble(xyz, new_xyz, features, idx, self.use_xyz)
+
+
+class QueryAndGroupDilated(nn.Module):
+    """(reference :427-463)"""
+
+    def __init__(self, radius_in: float, radius_out: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius_in, self.radius_out, self.nsample, self.use_xyz = radius_in, radius_out, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        idx_cnt, idx = ball_query_dilated(self.radius_in, self.radius_out, self.nsample, xyz, new_xyz)
+        return idx_cnt, _assemble(xyz, new_xyz, features, idx, self.use_xyz)
+
+
+class GroupAll(nn.Module):
+    """(reference :466-488) no kernel involved."""
+
+    def __init__(self, use_xyz: bool = True):
+        super().__init__()
+        self.use_xyz = use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is None:
+            return grouped_xyz
+        grouped_features = features.unsqueeze(2)
+        if self.use_xyz:
+            return torch.cat([grouped_xyz, grouped_features], dim=1)
+        return grouped_features

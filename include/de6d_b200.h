@@ -1,0 +1,158 @@
+/*
+ * de6d_b200.h -- C ABI of libde6d_b200.so: B200-native (sm_100a) point-set-abstraction and box ops for
+ * Det6D / SASA / 3DSSD style detectors.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one function of the reference's three pybind11
+ * extension modules (paths relative to core/pcdet/ops/ of HITSZ-NRSL/De6D):
+ *   pointnet2_batch_cuda   pointnet2/pointnet2_batch/src/pointnet2_api.cpp:11-30
+ *   iou3d_nms_cuda         iou3d_nms/src/iou3d_nms_api.cpp:11-17
+ *   roiaware_pool3d_cuda   roiaware_pool3d/src/roiaware_pool3d.cpp:172-177
+ * with the same argument order and meaning, minus the at::Tensor wrappers: plain device pointers, sizes,
+ * scalars and an explicit cudaStream_t (the reference launches on the legacy default stream).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to contiguous arrays on the current device, unless marked HOST;
+ *   - the caller owns and pre-initialises every output exactly like the reference Python wrappers do
+ *     (temp = 1e10, idx = 0, idx_cnt = 0, box index = -1, grads = 0); nothing is allocated inside;
+ *   - every function returns DE6D_OK (0) or an error code; de6d_last_error_string() describes the last
+ *     failure of the calling thread.  (The reference prints to stderr and exit(-1)s instead.)
+ *   - functions are asynchronous with respect to the host and re-entrant; no global state except the
+ *     per-kernel "max dynamic shared memory" attribute set on first use;
+ *   - results: indices / counts / keep lists are bit-identical to the reference kernels; floating-point
+ *     outputs are identical for the copy ops and three_interpolate, within 1e-5 relative for IoUs.
+ */
+#ifndef DE6D_B200_H
+#define DE6D_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_API_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+#define DE6D_OK 0
+#define DE6D_ERR_INVALID 1
+#define DE6D_ERR_CUDA 2
+
+const char *de6d_last_error_string(void);
+int de6d_version(void);
+const char *de6d_build_info(void);
+/* kernels launched through this library since it was loaded (diagnostic; bench.py reports it) */
+long long de6d_launch_count(void);
+
+/* ---- pointnet2_batch: sampling ------------------------------------------------------------------------- */
+
+/* farthest_point_sampling_wrapper(b, n, m, xyz, temp, idx)      sampling.cpp:41-50, sampling_gpu.cu:101-266
+ * xyz (b,n,3) f32; temp (b,n) f32 in/out running min squared distances (caller fills 1e10); idx (b,m) i32. */
+int de6d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx, cudaStream_t stream);
+
+/* furthest_point_sampling_matrix_wrapper(b, n, m, matrix, temp, idx)   sampling.cpp:52-61, sampling_gpu.cu:268-417
+ * matrix (b,n,n) f32 pairwise distances. */
+int de6d_furthest_point_sampling_matrix(int b, int n, int m, const float *matrix, float *temp, int *idx,
+                                        cudaStream_t stream);
+
+/* furthest_point_sampling_weights_wrapper(b, n, m, xyz, weights, temp, idx)   sampling.cpp:63-73, sampling_gpu.cu:419-585
+ * weights (b,n) f32; first index = argmax(weights). */
+int de6d_furthest_point_sampling_weights(int b, int n, int m, const float *xyz, const float *weights, float *temp,
+                                         int *idx, cudaStream_t stream);
+
+/* Same results, explicit kernel choice (testing / benchmarking): impl 0 = default, 1 = on-chip kernel with
+ * bucket pruning disabled, 2 = generic global-memory kernel. */
+int de6d_furthest_point_sampling_impl(int b, int n, int m, const float *xyz, float *temp, int *idx, int impl,
+                                      cudaStream_t stream);
+int de6d_furthest_point_sampling_weights_impl(int b, int n, int m, const float *xyz, const float *weights,
+                                              float *temp, int *idx, int impl, cudaStream_t stream);
+
+/* gather_points_wrapper(b, c, n, npoints, points, idx, out)   sampling.cpp:18-26, sampling_gpu.cu:16-52
+ * points (b,c,n), idx (b,npoints) -> out (b,c,npoints). */
+int de6d_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
+                       cudaStream_t stream);
+/* gather_points_grad_wrapper(b, c, n, npoints, grad_out, idx, grad_points)   sampling.cpp:29-38, sampling_gpu.cu:54-91
+ * accumulates into grad_points (b,c,n) (caller zeroes). */
+int de6d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                            float *grad_points, cudaStream_t stream);
+
+/* ---- pointnet2_batch: ball query ---------------------------------------------------------------------- */
+
+/* ball_query_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx)   ball_query.cpp:32-42, ball_query_gpu.cu:15-51
+ * NOTE argument order: new_xyz (b,m,3) before xyz (b,n,3).  idx (b,m,nsample) i32, caller zeroes. */
+int de6d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx,
+                    cudaStream_t stream);
+/* ball_query_cnt_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx_cnt, idx)   ball_query.cpp:44-55, ball_query_gpu.cu:93-130 */
+int de6d_ball_query_cnt(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                        int *idx_cnt, int *idx, cudaStream_t stream);
+/* ball_query_dilated_wrapper(b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx)
+ * ball_query.cpp:57-67, ball_query_gpu.cu:53-91 */
+int de6d_ball_query_dilated(int b, int n, int m, float radius_in, float radius_out, int nsample, const float *new_xyz,
+                            const float *xyz, int *idx_cnt, int *idx, cudaStream_t stream);
+
+/* ---- pointnet2_batch: grouping ------------------------------------------------------------------------ */
+
+/* group_points_wrapper(b, c, n, npoints, nsample, points, idx, out)   group_points.cpp:30-39, group_points_gpu.cu:53-92
+ * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample). */
+int de6d_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out,
+                      cudaStream_t stream);
+/* impl 0 = auto, 1 = direct-gather kernel, 2 = TMA-staged shared-memory kernel (identical results). */
+int de6d_group_points_impl(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
+                           float *out, int impl, cudaStream_t stream);
+/* group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out, idx, grad_points)   group_points.cpp:18-27, group_points_gpu.cu:14-51 */
+int de6d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
+                           float *grad_points, cudaStream_t stream);
+
+/* ---- pointnet2_batch: interpolation ------------------------------------------------------------------- */
+
+/* three_nn_wrapper(b, n, m, unknown, known, dist2, idx)   interpolate.cpp:21-30, interpolate_gpu.cu:16-81
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) SQUARED distances, idx (b,n,3). */
+int de6d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                  cudaStream_t stream);
+/* three_interpolate_wrapper(b, c, m, n, points, idx, weight, out)   interpolate.cpp:33-45, interpolate_gpu.cu:84-124 */
+int de6d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
+                           float *out, cudaStream_t stream);
+/* three_interpolate_grad_wrapper(b, c, n, m, grad_out, idx, weight, grad_points)   interpolate.cpp:48-58, interpolate_gpu.cu:127-168
+ * NOTE (b,c,n,m) order, as in the reference. */
+int de6d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight,
+                                float *grad_points, cudaStream_t stream);
+
+/* ---- iou3d_nms ---------------------------------------------------------------------------------------- */
+
+/* boxes_overlap_bev_gpu(boxes_a, boxes_b, ans_overlap)   iou3d_nms.cpp:49-68, iou3d_nms_kernel.cu:236-249
+ * boxes (N,7) [x,y,z,dx,dy,dz,heading] -> (na,nb) f32. */
+int de6d_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_overlap,
+                           cudaStream_t stream);
+/* boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou)   iou3d_nms.cpp:70-88, iou3d_nms_kernel.cu:251-265
+ * Also serves boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252): same arithmetic, run on the device. */
+int de6d_boxes_iou_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, cudaStream_t stream);
+/* Fused boxes_iou3d_gpu (python composition iou3d_nms_utils.py:48-81: BEV overlap x height overlap / union volume). */
+int de6d_boxes_iou3d(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, cudaStream_t stream);
+
+/* nms_gpu / nms_normal_gpu (iou3d_nms.cpp:90-186, kernels iou3d_nms_kernel.cu:267-372), batched and
+ * host-synchronisation free.  boxes (frames,n,7) sorted by descending score per frame; nvalid (frames) i32 or
+ * NULL (= n each): boxes at positions >= nvalid[f] are ignored.  normal != 0 selects the axis-aligned IoU.
+ * Outputs: keep (frames,n) int64 kept positions in ascending order (first num_keep[f] entries valid),
+ * num_keep (frames) i32.  workspace: de6d_nms_workspace_bytes(frames,n) bytes, initialised once by
+ * de6d_nms_workspace_init (the kernel leaves it reusable).  The reference's single-frame
+ * nms_gpu(boxes, keep HOST int64, thresh) -> num_to_keep is this call with frames = 1 plus a D2H copy. */
+size_t de6d_nms_workspace_bytes(int frames, int n);
+int de6d_nms_workspace_init(int frames, void *workspace, cudaStream_t stream);
+int de6d_nms_batched(int frames, int n, const float *boxes, const int *nvalid, float thresh, int normal,
+                     long long *keep, int *num_keep, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- roiaware_pool3d ---------------------------------------------------------------------------------- */
+
+/* points_in_boxes_gpu(boxes, pts, box_idx_of_points)   roiaware_pool3d.cpp:98-118, roiaware_pool3d_kernel.cu:313-359
+ * NOTE boxes (b,t,7) before pts (b,m,3).  out (b,m) i32, caller fills -1; value = first containing box. */
+int de6d_points_in_boxes(int b, int t, int m, const float *boxes, const float *pts, int *box_idx_of_points,
+                         cudaStream_t stream);
+/* points_in_boxes_cpu(boxes, pts, pts_indices)   roiaware_pool3d.cpp:143-168, run on the device:
+ * boxes (t,7), pts (m,3) -> (t,m) i32 0/1 mask, MARGIN 1e-2, host (unfused) arithmetic. */
+int de6d_points_in_boxes_mask(int t, int m, const float *boxes, const float *pts, int *point_indices,
+                              cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DE6D_B200_H */

@@ -1,0 +1,119 @@
+"""CPU suite: host-side logic -- sharding, the gloo gather path (world_size 2), chain configuration, the compat
+module registration, and that the ops refuse to run without CUDA tensors (no silent CPU path)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from de6d_b200 import dist as ddist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions():
+    for total in (0, 1, 7, 16, 512, 513):
+        for world in (1, 2, 4, 8):
+            spans = [ddist.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and b >= a
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, total, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = ddist.init_from_env(backend="gloo")
+    lo, hi = ddist.shard_range(total, r, w)
+    per = -(-total // w)
+    keep = torch.zeros((per, 4), dtype=torch.int64); num = torch.zeros(per, dtype=torch.int32)
+    for i, f in enumerate(range(lo, hi)):           # "detections" of frame f: f, f+1, ...
+        keep[i, : (f % 4) + 1] = torch.arange(f, f + (f % 4) + 1); num[i] = (f % 4) + 1
+    keep_all, num_all = ddist.gather_detections(keep, num)
+    t = ddist.max_over_ranks(float(rank + 1))
+    if rank == 0:
+        q.put((keep_all.numpy(), num_all.numpy(), t))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_gather_detections_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port, total, world = _free_port(), 6, 2
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    keep_all, num_all, t = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert t == 2.0
+    assert keep_all.shape == (6, 4)
+    for f in range(total):   # concatenated shards == what a single rank would have produced
+        n = (f % 4) + 1
+        assert num_all[f] == n
+        np.testing.assert_array_equal(keep_all[f, :n], np.arange(f, f + n))
+
+
+def test_chain_config_shapes():
+    from de6d_b200 import chain
+    cfg = chain.ChainConfig()
+    n = cfg.n_points
+    for layer in cfg.layers:
+        assert len(layer.npoints) == len(layer.methods) == len(layer.ranges)
+        for (lo, hi) in layer.ranges:
+            assert 0 <= lo < hi <= n
+        n = sum(layer.npoints)
+    assert n == 512 and cfg.n_votes <= n
+    host = chain.make_inputs(chain.small_config(), batch=2, seed=0, pinned=False)
+    assert host["xyz"].shape == (2, 2048, 3) and host["boxes"].shape == (2, 128, 7)
+    again = chain.make_inputs(chain.small_config(), batch=2, seed=0, pinned=False)
+    assert all(torch.equal(host[k], again[k]) for k in host)
+
+
+def test_compat_install_registers_reference_module_paths(lib):
+    from de6d_b200 import compat
+    names = compat.install()
+    assert set(names) == {"pcdet.ops.pointnet2.pointnet2_batch.pointnet2_batch_cuda", "pcdet.ops.iou3d_nms.iou3d_nms_cuda",
+                          "pcdet.ops.roiaware_pool3d.roiaware_pool3d_cuda"}
+    p2 = sys.modules["pcdet.ops.pointnet2.pointnet2_batch.pointnet2_batch_cuda"]
+    for fn in ("ball_query_wrapper", "ball_query_cnt_wrapper", "ball_query_dilated_wrapper", "group_points_wrapper",
+               "group_points_grad_wrapper", "gather_points_wrapper", "gather_points_grad_wrapper",
+               "farthest_point_sampling_wrapper", "furthest_point_sampling_matrix_wrapper",
+               "furthest_point_sampling_weights_wrapper", "three_nn_wrapper", "three_interpolate_wrapper",
+               "three_interpolate_grad_wrapper"):
+        assert callable(getattr(p2, fn))
+    for k in list(names):
+        sys.modules.pop(k, None)
+
+
+def test_ops_reject_cpu_tensors_instead_of_falling_back(lib):
+    from de6d_b200.compat import pointnet2_batch_cuda as p2, iou3d_nms_cuda as iou
+    xyz = torch.zeros(1, 8, 3); temp = torch.zeros(1, 8); idx = torch.zeros(1, 2, dtype=torch.int32)
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        p2.farthest_point_sampling_wrapper(1, 8, 2, xyz, temp, idx)
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        iou.boxes_iou_bev_gpu(torch.zeros(2, 7), torch.zeros(2, 7), torch.zeros(2, 2))
+
+
+def test_mirror_modules_expose_reference_names(lib):
+    from de6d_b200 import pointnet2_utils as pu, iou3d_nms_utils as iu, roiaware_pool3d_utils as ru
+    for name in ("furthest_point_sample", "farthest_point_sample", "furthest_point_sample_matrix", "furthest_point_sample_weights",
+                 "calc_dist_matrix_for_sampling", "gather_operation", "three_nn", "three_interpolate", "grouping_operation",
+                 "ball_query", "ball_query_cnt", "ball_query_dilated", "QueryAndGroup", "QueryWithCntAndGroup",
+                 "QueryAndGroupDilated", "GroupAll"):
+        assert hasattr(pu, name), name
+    for name in ("boxes_bev_iou_cpu", "boxes_iou_bev", "boxes_iou3d_gpu", "nms_gpu", "nms_normal_gpu"):
+        assert hasattr(iu, name), name
+    for name in ("points_in_boxes_cpu", "points_in_boxes_gpu"):
+        assert hasattr(ru, name), name
