@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the Det6D SA + NMS op chain (BASELINE.json metric: frames/s for the 16384-point chain).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]          # this package on N B200s
+    python bench.py --impl reference [...]                                    # the CPU path on the host cores
+
+A step = one pass of the op chain (de6d_b200.chain.OpChain: 3 SA layers with D-/F-/S-FPS, gather, ball_query_cnt
++ grouping per radius scale, the head's vote grouping, batched rotated NMS on 512 proposals/frame) over one
+batch of synthetic KITTI-shape frames.  Per GPU the batch is BASELINE.json configs[2] (64 frames); frames are
+sharded across ranks with no data-path collective (weak scaling: 8 GPUs x 64 = configs[3]'s 512 frames).
+
+One JSON line on stdout (rank 0):
+  value     frames/s, inputs resident in HBM, CUDA-graph replay, CUDA events on the launching stream, max over ranks
+  e2e       frames/s through OpChain.step_host: pinned host inputs -> H2D -> chain -> D2H of the results, every step
+  roofline  dominant kernel (by measured time) against the measured HBM peak; `kernels` lists every entry point
+  cpu_baseline  the oracle (CPU restatement of the reference kernels) on a bounded sample of the same workload
+oracle/ is used here only as that CPU baseline / the --impl reference arm, never on the measured GPU path.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames_per_second_16384pt_SA_NMS_op_chain"
+UNIT = "frames/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(name, a):
+    """Compulsory HBM bytes of one launch (DESIGN.md 'Algorithmic bytes'), from the C-ABI arguments."""
+    if name in ("de6d_furthest_point_sampling", "de6d_furthest_point_sampling_impl"):
+        b, n, m = a[0], a[1], a[2]
+        return b * (12 * n + 4 * m)
+    if name in ("de6d_furthest_point_sampling_weights", "de6d_furthest_point_sampling_weights_impl"):
+        b, n, m = a[0], a[1], a[2]
+        return b * (16 * n + 4 * m)
+    if name == "de6d_furthest_point_sampling_matrix":
+        b, n, m = a[0], a[1], a[2]
+        return b * (4 * n * m + 4 * m)
+    if name == "de6d_gather_points":
+        b, c, n, npnt = a[0], a[1], a[2], a[3]
+        return b * (4 * npnt + 8 * c * npnt)
+    if name in ("de6d_ball_query", "de6d_ball_query_cnt"):
+        b, n, m, ns = a[0], a[1], a[2], a[4]
+        return b * (12 * n + 12 * m + 4 * m * ns + (4 * m if name.endswith("cnt") else 0))
+    if name == "de6d_ball_query_dilated":
+        b, n, m, ns = a[0], a[1], a[2], a[5]
+        return b * (12 * n + 12 * m + 4 * m * ns + 4 * m)
+    if name in ("de6d_group_points", "de6d_group_points_impl"):
+        b, c, n, npnt, ns = a[0], a[1], a[2], a[3], a[4]
+        return b * (4 * npnt * ns + 4 * c * min(n, npnt * ns) + 4 * c * npnt * ns)
+    if name == "de6d_nms_batched":
+        frames, n = a[0], a[1]
+        return frames * 36 * n
+    return 0
+
+
+class ClockSampler:
+    """Samples SM clock and clock-event (throttle) reasons of one GPU while the timed regions run."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clocks_setting",
+               0x10: "sync_boost"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_one_frame(args):
+    """Worker: the oracle chain on one frame (single thread)."""
+    batch_seed, frame = args
+    import torch
+    torch.set_num_threads(1)
+    from de6d_b200 import chain as ch
+    from oracle import chain_ref
+    host = _cpu_one_frame.cache.get(batch_seed)
+    if host is None:
+        host = ch.make_inputs(ch.ChainConfig(), _cpu_one_frame.batch, seed=batch_seed, pinned=False)
+        _cpu_one_frame.cache = {batch_seed: host}
+    t0 = time.perf_counter()
+    chain_ref.run_chain(ch.ChainConfig(), host, frames=slice(frame, frame + 1))
+    return time.perf_counter() - t0
+
+
+_cpu_one_frame.cache = {}
+_cpu_one_frame.batch = 16
+
+
+def cpu_baseline_single_core(budget_s=12.0, max_frames=16):
+    """Oracle port, one core, frame after frame until ~budget_s of CPU work is done."""
+    from oracle import oracle
+    oracle.build()
+    _cpu_one_frame((0, 0))  # warm-up: builds inputs, pages the library in
+    t, frames = 0.0, 0
+    while t < budget_s and frames < max_frames:
+        t += _cpu_one_frame((0, frames % _cpu_one_frame.batch))
+        frames += 1
+    return {"value": frames / t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d frames of the same chain config, oracle (C restatement of the reference kernels, -O2) on one host core, %.1f s" % (frames, t)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU path on all host cores.  The reference ships no CPU implementation of FPS, ball
+    query, grouping or NMS (CUDA only), so the CPU arm is the oracle port run frame-parallel over a process pool."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    from oracle import oracle
+    oracle.build()
+    cores = len(os.sched_getaffinity(0))
+    per_step = cores
+    ctx = mp.get_context("fork")
+    with ProcessPoolExecutor(max_workers=cores, mp_context=ctx) as ex:
+        def step(nframes):
+            t0 = time.perf_counter()
+            list(ex.map(_cpu_one_frame, [(0, i % _cpu_one_frame.batch) for i in range(nframes)]))
+            return time.perf_counter() - t0
+        step(cores)                                     # pool start-up + input generation in every worker
+        t_probe = step(per_step)
+        budget = 240.0
+        total_steps = args.steps + max(args.warmup - 1, 0)
+        if t_probe * total_steps > budget:              # keep the whole run within a few minutes
+            per_step = max(1, int(per_step * budget / (t_probe * total_steps)))
+        for _ in range(max(args.warmup - 1, 0)):
+            step(per_step)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(per_step)
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.batch, max(args.gpus, 1),
+                                  note="CPU arm: each step is a bounded sample of %d frames of this workload" % per_step),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d frames per step, one oracle process per host core (%d), %d steps" % (per_step, cores, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, batch, world, note=None):
+    from de6d_b200 import chain as ch
+    cfg = ch.ChainConfig()
+    c = {
+        "workload": "Det6D/SASA SA chain 16384->4096->1024->512 (D-FPS+F-FPS+S-FPS, ball_query_cnt+group per scale) "
+                    "+ vote grouping + rotated NMS on %d proposals/frame; %d frames per GPU (BASELINE configs[2]; x8 GPUs = configs[3])"
+                    % (cfg.n_proposals, batch),
+        "points_per_frame": cfg.n_points, "frames_per_gpu": batch, "global_frames": batch * world,
+        "sharding": "frames x%d, no data-path collective" % world,
+        "layers": [{"npoints": l.npoints, "methods": l.methods, "radii": l.radii, "nsamples": l.nsamples, "c_in": l.c_in}
+                   for l in cfg.layers],
+        "nms_thresh": cfg.nms_thresh,
+    }
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from de6d_b200 import build as de6d_build
+    de6d_build.build()
+    from de6d_b200 import _lib, chain as ch, dist as ddist
+
+    rank, world, local = ddist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the op chain has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = ch.ChainConfig()
+    batch = args.batch
+    host = ch.make_inputs(cfg, batch, seed=rank)
+
+    chain = ch.OpChain(cfg, batch, device=dev)
+    chain.load(host)
+    chain.capture()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out_bytes = sum(v.numel() * v.element_size() for k, v in chain.outputs.items() if isinstance(v, torch.Tensor))
+    clocks = ClockSampler(local)
+
+    # ---- device-resident timed region --------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        chain.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.start()
+    e0.record(chain.main)
+    for _ in range(args.steps):
+        chain.step()
+    e1.record(chain.main)
+    barrier()
+    ms = ddist.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    # ---- end to end: pinned host inputs -> H2D -> chain -> D2H, every step ------------------------------------
+    for _ in range(3):
+        chain.step_host(host)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(chain.main)
+    for _ in range(args.steps):
+        chain.step_host(host, sync=True)
+    f1.record(chain.main)
+    barrier()
+    clocks.stop()
+    ms_e2e = ddist.max_over_ranks(f0.elapsed_time(f1), dev)
+    frames_global = batch * world
+
+    # ---- per entry-point timing (rank 0): the same chain, one stream, eager, CUDA events around every launch -----
+    kernels, roofline, fps_us = [], None, None
+    if rank == 0:
+        prof = ch.OpChain(cfg, batch, device=dev, use_graph=False, serial=True)
+        prof.load(host)
+        prof.capture()                      # eager warm-up (use_graph=False: nothing is captured)
+        torch.cuda.synchronize()
+        reps = 5
+        _lib.trace_begin()
+        for _ in range(reps):
+            prof.step()
+        trace = _lib.trace_end()
+        agg = {}
+        for name, a, t in trace:
+            key = (name, tuple(x for x in a if isinstance(x, int) and not isinstance(x, bool) and abs(x) < (1 << 31))[:6])
+            d = agg.setdefault(key, {"ms": 0.0, "launches": 0, "bytes": algorithmic_bytes(name, a)})
+            d["ms"] += t
+            d["launches"] += 1
+        peak, peak_src = measured_peaks()
+        by_name = {}
+        for (name, shape), d in agg.items():
+            avg = d["ms"] / d["launches"]
+            gbs = d["bytes"] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+            kernels.append({"entry": name, "shape": list(shape), "ms_per_launch": round(avg, 5),
+                            "launches_per_step": d["launches"] // reps, "alg_bytes": d["bytes"],
+                            "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)})
+            by_name.setdefault(name, 0.0)
+            by_name[name] += d["ms"] / reps
+        kernels.sort(key=lambda k: -k["ms_per_launch"] * k["launches_per_step"])
+        total_ms = sum(by_name.values())
+        top = kernels[0]
+        roofline = {"kernel": top["entry"], "shape": top["shape"], "bound": "hbm", "achieved": top["gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": top["ms_per_launch"],
+                    "share_of_step": round(top["ms_per_launch"] * top["launches_per_step"] / total_ms, 4) if total_ms else None,
+                    "note": "dominant entry point by time; timed alone (single stream, eager) with CUDA events on its stream"}
+        for k in kernels:   # the HBM-bound gather with the largest output: the >=60 %-of-roofline target of north_star
+            if k["entry"] == "de6d_group_points":
+                if "group_points" not in roofline or k["alg_bytes"] > roofline["group_points"]["alg_bytes"]:
+                    roofline["group_points"] = {"shape": k["shape"], "alg_bytes": k["alg_bytes"], "achieved": k["gbs"],
+                                                "frac": k["frac_hbm"], "ms_per_launch": k["ms_per_launch"]}
+            if k["entry"] == "de6d_furthest_point_sampling" and k["shape"][1] == cfg.n_points:
+                fps_us = 1e3 * k["ms_per_launch"] / batch
+        del prof
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single_core(args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": frames_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, batch, world,
+                                      note="L2: per-step working set %.0f MB of inputs+outputs >> 126 MB L2, no explicit flush" % (
+                                          (out_bytes + chain.h2d_bytes()) / 1e6)),
+            "e2e": {"value": frames_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": chain.h2d_bytes(), "d2h_bytes_per_step": chain.d2h_bytes(),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(chain.kernels_per_step) * args.steps,
+            "gpu_launches_note": "%d launches of this library's kernels per step (counted by de6d_launch_count on the eager "
+                                 "warm-up pass) replayed from one CUDA graph per step" % chain.kernels_per_step,
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "fps_us_per_frame": fps_us,
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--impl", default="de6d_b200", choices=["de6d_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

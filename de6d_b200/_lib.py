@@ -77,10 +77,39 @@ def load():
     return lib
 
 
+_trace = None   # None, or a list of (entry point, args, start event, end event) filled by call()
+
+
+def trace_begin():
+    """Start bracketing every entry-point call with CUDA events on the stream it is launched on (bench.py's
+    per-kernel timing pass; not for use inside CUDA-graph capture)."""
+    global _trace
+    _trace = []
+
+
+def trace_end():
+    """Stop tracing and return [(name, args, milliseconds)]; synchronises the device."""
+    global _trace
+    import torch
+    torch.cuda.synchronize()
+    out = [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in (_trace or [])]
+    _trace = None
+    return out
+
+
 def call(name, *args):
     """Invoke a status-returning entry point; raise De6dError with the library's message on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _trace is not None:
+        import torch
+        s = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        rc = getattr(lib, name)(*args)
+        e1.record(s)
+        _trace.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise De6dError("%s failed (code %d): %s" % (name, rc, lib.de6d_last_error_string().decode()))
 

@@ -105,14 +105,18 @@ class OpChain:
     N_SIDE = 4
 
     def __init__(self, cfg: ChainConfig, batch: int, device: Optional[torch.device] = None, use_graph: bool = True,
-                 keep_matrices: bool = False):
+                 keep_matrices: bool = False, serial: bool = False):
         self.cfg, self.batch = cfg, batch
         self.keep_matrices = keep_matrices   # tests: expose the F-FPS distance matrices fed to the kernel
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.use_graph = use_graph
         self.main = torch.cuda.Stream(self.device)
-        self.side = [torch.cuda.Stream(self.device) for _ in range(self.N_SIDE)]   # grouping, one per scale
-        self.samp = [torch.cuda.Stream(self.device) for _ in range(2)]             # extra sampling methods
+        if serial:   # everything on one stream (per-kernel timing pass of bench.py, ncu launch lists)
+            self.side = [self.main] * self.N_SIDE
+            self.samp = [self.main] * 2
+        else:
+            self.side = [torch.cuda.Stream(self.device) for _ in range(self.N_SIDE)]   # grouping, one per scale
+            self.samp = [torch.cuda.Stream(self.device) for _ in range(2)]             # extra sampling methods
         self.inputs = None          # static device copies
         self.outputs = None         # static device outputs of the last captured step
         self.graph = None
@@ -208,6 +212,7 @@ class OpChain:
                 xyz_flipped = xyz.transpose(1, 2).contiguous()
                 new_xyz = pu.gather_operation(xyz_flipped, sample_idx).transpose(1, 2).contiguous()
                 outs["l%d_idx" % li] = sample_idx
+                outs["l%d_new_xyz" % li] = new_xyz   # also keeps the block alive while side streams read it
                 sampled = torch.cuda.Event()
                 sampled.record(main)
                 grouped_done = self._group_scales(xyz, new_xyz, feats, layer.radii, layer.nsamples, sampled, outs, "l%d" % li)
@@ -217,6 +222,7 @@ class OpChain:
             for ev in pending:
                 main.wait_event(ev)
             votes = (xyz[:, :cfg.n_votes, :] + inp["vote_offsets"]).contiguous()
+            outs["votes"] = votes
             ready = torch.cuda.Event()
             ready.record(main)
             head_done = self._group_scales(xyz, votes, inp["vote_feats"], cfg.vote_radii, cfg.vote_nsamples, ready, outs, "head")
