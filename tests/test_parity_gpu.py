@@ -231,17 +231,25 @@ def test_iou_matrices_vs_oracle(orc, ops, seed):
     np.testing.assert_allclose(got_cpu_api, want, rtol=RTOL_IOU, atol=1e-7)
 
 
+def _nms_case(orc, seed, n, thr):
+    """Seeded proposals with no pair within 1e-4 of the threshold: keep lists are only required to be identical
+    when no IoU sits inside the 1e-5 tolerance band of the threshold (hard part 2).  Seeds are walked
+    deterministically (seed, seed+100, ...) until the oracle's own IoU matrix is clear of the band."""
+    for s in range(seed, seed + 2000, 100):
+        bx, sc = synth.proposals(1, n, seed=s, clusters=max(n // 8, 1))
+        bx, sc = bx[0], sc[0]
+        order = np.argsort(-sc, kind="stable")
+        sb = np.ascontiguousarray(bx[order])
+        if not _near_threshold(orc.boxes_iou_bev(sb, sb), thr, eps=1e-4).any():
+            return bx, sc, order, sb
+    raise AssertionError("no clean seed found")
+
+
 @pytest.mark.parametrize("seed,n,thr", [(0, 512, 0.01), (1, 512, 0.1), (2, 300, 0.5), (3, 64, 0.1), (4, 65, 0.1), (5, 1, 0.1), (6, 1500, 0.3)])
 def test_nms_vs_oracle(orc, ops, seed, n, thr):
     iu = ops[1]
-    bx, sc = synth.proposals(1, n, seed=seed, clusters=max(n // 8, 1))
-    bx, sc = bx[0], sc[0]
-    order = np.argsort(-sc, kind="stable")
-    sb = np.ascontiguousarray(bx[order])
-    want_keep, want_mask = orc.nms_sorted(sb, thr, return_mask=True)
-    # exactness is only meaningful when no pair sits within the IoU tolerance of the threshold (hard part 2)
-    iou = orc.boxes_iou_bev(sb, sb)
-    assert not _near_threshold(iou, thr).any(), "seed has a near-threshold pair; pick another seed"
+    bx, sc, order, sb = _nms_case(orc, seed, n, thr)
+    want_keep = orc.nms_sorted(sb, thr)
     keep, _ = iu.nms_gpu(cu(bx), cu(sc), thr)
     np.testing.assert_array_equal(keep.cpu().numpy(), order[want_keep])
     keepn, _ = iu.nms_normal_gpu(cu(bx), cu(sc), thr)
