@@ -142,7 +142,7 @@ def _cpu_one_frame(args):
         host = ch.make_inputs(ch.ChainConfig(), _cpu_one_frame.batch, seed=batch_seed, pinned=False)
         _cpu_one_frame.cache = {batch_seed: host}
     t0 = time.perf_counter()
-    chain_ref.run_chain(ch.ChainConfig(), host, frames=slice(frame, frame + 1))
+    chain_ref.run_chain(ch.ChainConfig(), host, frames=slice(frame, frame + 1), ffps_matrix="torch")
     return time.perf_counter() - t0
 
 

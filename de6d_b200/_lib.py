@@ -21,11 +21,14 @@ PROTOTYPES = {
     "de6d_furthest_point_sampling_weights": [_i, _i, _i, _p, _p, _p, _p, _p],
     "de6d_furthest_point_sampling_impl": [_i, _i, _i, _p, _p, _p, _i, _p],
     "de6d_furthest_point_sampling_weights_impl": [_i, _i, _i, _p, _p, _p, _p, _i, _p],
+    "de6d_dist_matrix": [_i, _i, _i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _f, _p, _p],
     "de6d_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_ball_query": [_i, _i, _i, _f, _i, _p, _p, _p, _p],
     "de6d_ball_query_cnt": [_i, _i, _i, _f, _i, _p, _p, _p, _p, _p],
     "de6d_ball_query_dilated": [_i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p],
+    "de6d_ball_query_workspace_bytes": [_i, _i],
+    "de6d_ball_query_ex": [_i, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _sz, _p],
     "de6d_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_group_points_impl": [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     "de6d_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
@@ -47,6 +50,7 @@ PROTOTYPES = {
 }
 _RESTYPES = {
     "de6d_nms_workspace_bytes": _sz,
+    "de6d_ball_query_workspace_bytes": _sz,
     "de6d_last_error_string": C.c_char_p,
     "de6d_build_info": C.c_char_p,
     "de6d_launch_count": C.c_longlong,

@@ -3,30 +3,36 @@ Same names, same positional arguments, tensors pre-allocated by the caller; ever
 the reference wrappers do.  `grid_query_wrapper` is not provided: no Python code in the reference calls it."""
 import torch
 
+from .._lib import load
 from ._common import call, dev, need, stream_ptr
 
 f32, i32 = torch.float32, torch.int32
 
 
-def ball_query_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx):
+def _ball_query(mode, b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, impl=0):
+    """All three variants go through de6d_ball_query_ex with scratch from torch's allocator (stream-ordered on the
+    current stream, CUDA-graph capturable)."""
     need(new_xyz, b * m * 3, "new_xyz"); need(xyz, b * n * 3, "xyz"); need(idx, b * m * nsample, "idx")
-    call("de6d_ball_query", b, n, m, radius, nsample, dev(new_xyz, "new_xyz", f32), dev(xyz, "xyz", f32),
-         dev(idx, "idx", i32), stream_ptr())
+    if idx_cnt is not None:
+        need(idx_cnt, b * m, "idx_cnt")
+    ws_bytes = int(load().de6d_ball_query_workspace_bytes(b, n)) if impl == 0 else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device) if ws_bytes else None
+    call("de6d_ball_query_ex", mode, impl, b, n, m, radius_in, radius_out, nsample, dev(new_xyz, "new_xyz", f32),
+         dev(xyz, "xyz", f32), None if idx_cnt is None else dev(idx_cnt, "idx_cnt", i32), dev(idx, "idx", i32),
+         None if ws is None else ws.data_ptr(), ws_bytes, stream_ptr())
     return 1
+
+
+def ball_query_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx):
+    return _ball_query(0, b, n, m, 0.0, radius, nsample, new_xyz, xyz, None, idx)
 
 
 def ball_query_cnt_wrapper(b, n, m, radius, nsample, new_xyz, xyz, idx_cnt, idx):
-    need(new_xyz, b * m * 3, "new_xyz"); need(xyz, b * n * 3, "xyz"); need(idx, b * m * nsample, "idx"); need(idx_cnt, b * m, "idx_cnt")
-    call("de6d_ball_query_cnt", b, n, m, radius, nsample, dev(new_xyz, "new_xyz", f32), dev(xyz, "xyz", f32),
-         dev(idx_cnt, "idx_cnt", i32), dev(idx, "idx", i32), stream_ptr())
-    return 1
+    return _ball_query(1, b, n, m, 0.0, radius, nsample, new_xyz, xyz, idx_cnt, idx)
 
 
 def ball_query_dilated_wrapper(b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx):
-    need(new_xyz, b * m * 3, "new_xyz"); need(xyz, b * n * 3, "xyz"); need(idx, b * m * nsample, "idx"); need(idx_cnt, b * m, "idx_cnt")
-    call("de6d_ball_query_dilated", b, n, m, radius_in, radius_out, nsample, dev(new_xyz, "new_xyz", f32),
-         dev(xyz, "xyz", f32), dev(idx_cnt, "idx_cnt", i32), dev(idx, "idx", i32), stream_ptr())
-    return 1
+    return _ball_query(2, b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx)
 
 
 def group_points_wrapper(b, c, n, npoints, nsample, points, idx, out):

@@ -11,6 +11,7 @@
 // order is preserved without any sort and a warp stops as soon as its Q balls are full.  Hit lists are
 // collected in shared memory and written as whole rows (128 B for nsample = 32).
 #include "common.cuh"
+#include <math.h>
 
 namespace de6d {
 
@@ -112,24 +113,328 @@ ball_query_kernel(int n, int m, float r2_in, float r2_out, int nsample, const fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Grid path (large clouds, balls that are small against the cloud: the SA layers' regime).
+//
+// The brute-force kernel above tests every (query, point) pair: 4.3 G distance tests per launch at 64 frames x
+// 4096 queries x 16384 points, and on sparse clouds no ball ever fills, so there is no early exit.  Here a
+// uniform grid is built per cloud (one CTA per cloud: bounding box, cell size >= the padded radius chosen so the
+// grid has at most BQG_CAP cells, shared-memory histogram, scan, scatter of (x, y, z, index) records).  A query
+// then only tests the points of the <= 3x3x3 cells its padded bounding cube touches -- with the SAME rounded
+// distance expression -- and keeps the `nsample` smallest indices among the hits in a sorted list, so the result
+// is the first `nsample` hits in ascending index order exactly as the reference's serial scan produces them.
+//
+// Exactness of the candidate set: every term of d2 = fl(dz^2 + fl(dx^2 + fl(dy^2))) is non-negative and rounding
+// is monotone, so d2 < r2 implies fl(da^2) < r2 for each axis a, hence |q_a - p_a| <= r (1 + 2^-21).  The query's
+// cell range is computed from fl(q_a -+ R') with R' = 1.0001 r + 1e-6 (|q_a| + r), which brackets that interval
+// even after the rounding of the subtraction, and the cell function (float subtract, multiply, floor, clamp) is
+// monotone, so every point that can pass the test lies in a visited cell.  Points visited but outside the ball
+// fail the exact test.  Queries whose candidate count exceeds `cand_limit` (balls that swallow a large part of
+// the cloud) and clouds with a non-finite bounding box fall back to the reference's in-order scan with early
+// exit, inside the same kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BQG_CAP = 32768;          // max cells per cloud (128 KB histogram in shared memory)
+constexpr int BQG_BUILD_T = 1024;
+constexpr int BQG_QT = 256;
+
+struct BQGridHeader {
+    float ox, oy, oz, inv_c;
+    int dimx, dimy, dimz, valid;
+};
+
+__host__ __device__ inline size_t bqg_ws_per_cloud(int n) {
+    size_t bytes = sizeof(BQGridHeader) + sizeof(int) * (size_t)(BQG_CAP + 4) + 16 * (size_t)n;
+    return (bytes + 255) & ~(size_t)255;
+}
+
+__device__ __forceinline__ int bqg_cell(float v, float o, float inv_c, int dim) {
+    const int c = __float2int_rd(__fmul_rn(__fsub_rn(v, o), inv_c));   // saturating, NaN -> 0
+    return min(max(c, 0), dim - 1);
+}
+
+__global__ void __launch_bounds__(BQG_BUILD_T)
+bq_grid_build_kernel(int n, float r_abs, const float *__restrict__ xyz_all, unsigned char *__restrict__ ws_all,
+                     size_t ws_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *cnt = reinterpret_cast<int *>(smem_raw);            // [BQG_CAP] histogram, then scatter cursors
+    __shared__ float red[6][BQG_BUILD_T / 32];
+    __shared__ int wsum[BQG_BUILD_T / 32];
+    __shared__ BQGridHeader sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
+    unsigned char *ws = ws_all + (size_t)blockIdx.x * ws_stride;
+    BQGridHeader *hdr = reinterpret_cast<BQGridHeader *>(ws);
+    int *cell_start = reinterpret_cast<int *>(ws + sizeof(BQGridHeader));
+    float4 *sorted = reinterpret_cast<float4 *>(ws + sizeof(BQGridHeader) + sizeof(int) * (size_t)(BQG_CAP + 4));
+
+    // ---- bounding box ----
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+    for (int k = tid; k < n; k += BQG_BUILD_T) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = xyz[(size_t)k * 3 + a];
+            bad |= !(fabsf(v) <= 1.0e30f);
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { red[a][w] = lo[a]; red[3 + a][w] = hi[a]; }
+    }
+    const int anybad = __syncthreads_or(bad ? 1 : 0);
+    if (tid == 0) {
+        float l[3], e[3];
+        for (int a = 0; a < 3; ++a) {
+            float mn = INFINITY, mx = -INFINITY;
+            for (int i = 0; i < BQG_BUILD_T / 32; ++i) { mn = fminf(mn, red[a][i]); mx = fmaxf(mx, red[3 + a][i]); }
+            l[a] = mn; e[a] = mx - mn;
+        }
+        BQGridHeader h;
+        h.valid = (n > 0 && !anybad && r_abs == r_abs && r_abs <= 1.0e30f) ? 1 : 0;
+        float c = fmaxf(r_abs * 1.0002f, 1e-20f);
+        // smallest cell size >= the padded radius with at most BQG_CAP cells
+        int dx = 1, dy = 1, dz = 1;
+        if (h.valid) {
+            for (int it = 0; it < 400; ++it) {
+                const float fx = e[0] / c, fy = e[1] / c, fz = e[2] / c;
+                if (fx < 30000.f && fy < 30000.f && fz < 30000.f) {
+                    dx = (int)fx + 1; dy = (int)fy + 1; dz = (int)fz + 1;
+                    if ((long long)dx * dy * dz <= BQG_CAP) break;
+                }
+                c *= 1.2f;
+                dx = dy = dz = 1;
+            }
+            if ((long long)dx * dy * dz > BQG_CAP) { dx = dy = dz = 1; }
+        }
+        h.ox = l[0]; h.oy = l[1]; h.oz = l[2];
+        h.inv_c = 1.0f / c;
+        h.dimx = dx; h.dimy = dy; h.dimz = dz;
+        sh = h;
+        *hdr = h;
+    }
+    __syncthreads();
+    const BQGridHeader h = sh;
+    if (!h.valid) return;
+    const int ncell = h.dimx * h.dimy * h.dimz;
+
+    // ---- histogram ----
+    for (int i = tid; i < ncell; i += BQG_BUILD_T) cnt[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < n; k += BQG_BUILD_T) {
+        const float x = xyz[(size_t)k * 3], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
+        const int c = (bqg_cell(z, h.oz, h.inv_c, h.dimz) * h.dimy + bqg_cell(y, h.oy, h.inv_c, h.dimy)) * h.dimx +
+                      bqg_cell(x, h.ox, h.inv_c, h.dimx);
+        atomicAdd(&cnt[c], 1);
+    }
+    __syncthreads();
+
+    // ---- exclusive scan over ncell entries: thread t owns a contiguous chunk ----
+    const int chunk = ceil_div(ncell, BQG_BUILD_T);
+    const int c0 = min(tid * chunk, ncell), c1 = min(c0 + chunk, ncell);
+    int sum = 0;
+    for (int i = c0; i < c1; ++i) sum += cnt[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int v = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        wsum[lane] = v;
+    }
+    __syncthreads();
+    int run = incl - sum + (w ? wsum[w - 1] : 0);
+    for (int i = c0; i < c1; ++i) {
+        const int c = cnt[i];
+        cnt[i] = run;          // becomes the scatter cursor
+        cell_start[i] = run;
+        run += c;
+    }
+    if (tid == BQG_BUILD_T - 1) cell_start[ncell] = n;
+    __syncthreads();
+
+    // ---- scatter (order inside a cell is irrelevant: the query keeps the smallest indices) ----
+    for (int k = tid; k < n; k += BQG_BUILD_T) {
+        const float x = xyz[(size_t)k * 3], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
+        const int c = (bqg_cell(z, h.oz, h.inv_c, h.dimz) * h.dimy + bqg_cell(y, h.oy, h.inv_c, h.dimy)) * h.dimx +
+                      bqg_cell(x, h.ox, h.inv_c, h.dimx);
+        const int pos = atomicAdd(&cnt[c], 1);
+        sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(BQG_QT)
+bq_grid_query_kernel(int n, int m, float r_abs, float r2_in, float r2_out, int nsample, int cand_limit,
+                     const float *__restrict__ new_xyz, const float *__restrict__ xyz,
+                     const unsigned char *__restrict__ ws_all, size_t ws_stride, int *__restrict__ idx_cnt,
+                     int *__restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *lists = reinterpret_cast<int *>(smem_raw);   // [BQG_QT][nsample + 1] (odd pitch: conflict-free per-thread rows)
+    const int pitch = nsample | 1;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int bs = blockIdx.y;
+    const int q = blockIdx.x * BQG_QT + tid;
+    xyz += (size_t)bs * n * 3;
+    new_xyz += (size_t)bs * m * 3;
+    const unsigned char *ws = ws_all + (size_t)bs * ws_stride;
+    const BQGridHeader h = *reinterpret_cast<const BQGridHeader *>(ws);
+    const int *cell_start = reinterpret_cast<const int *>(ws + sizeof(BQGridHeader));
+    const float4 *sorted = reinterpret_cast<const float4 *>(ws + sizeof(BQGridHeader) + sizeof(int) * (size_t)(BQG_CAP + 4));
+    int *list = lists + (size_t)tid * pitch;
+
+    int L = 0;
+    if (q < m && nsample > 0) {
+        const float qx = new_xyz[(size_t)q * 3], qy = new_xyz[(size_t)q * 3 + 1], qz = new_xyz[(size_t)q * 3 + 2];
+        bool serial = !h.valid;
+        if (!serial) {
+            const float px = __fmaf_rn(1e-6f, fabsf(qx) + r_abs, r_abs * 1.0001f);
+            const float py = __fmaf_rn(1e-6f, fabsf(qy) + r_abs, r_abs * 1.0001f);
+            const float pz = __fmaf_rn(1e-6f, fabsf(qz) + r_abs, r_abs * 1.0001f);
+            const int ix0 = bqg_cell(__fsub_rn(qx, px), h.ox, h.inv_c, h.dimx), ix1 = bqg_cell(__fadd_rn(qx, px), h.ox, h.inv_c, h.dimx);
+            const int iy0 = bqg_cell(__fsub_rn(qy, py), h.oy, h.inv_c, h.dimy), iy1 = bqg_cell(__fadd_rn(qy, py), h.oy, h.inv_c, h.dimy);
+            const int iz0 = bqg_cell(__fsub_rn(qz, pz), h.oz, h.inv_c, h.dimz), iz1 = bqg_cell(__fadd_rn(qz, pz), h.oz, h.inv_c, h.dimz);
+            int seen = 0;
+            int last = 0x7fffffff;   // largest index in a full list
+            for (int iz = iz0; iz <= iz1 && !serial; ++iz) {
+                for (int iy = iy0; iy <= iy1; ++iy) {
+                    const int row = (iz * h.dimy + iy) * h.dimx;
+                    const int s = __ldg(cell_start + row + ix0), e = __ldg(cell_start + row + ix1 + 1);
+                    seen += e - s;
+                    if (seen > cand_limit) { serial = true; break; }
+                    for (int i = s; i < e; ++i) {
+                        const float4 p = __ldg(sorted + i);
+                        const int k = __float_as_int(p.w);
+                        if (k > last) continue;   // list is full and this index cannot enter it
+                        const float d2 = sqdist(qx, qy, qz, p.x, p.y, p.z);
+                        bool hit = d2 < r2_out;
+                        if (MODE == BQ_DILATED) hit = hit && (d2 >= r2_in);
+                        if (!hit) continue;
+                        int pos = (L < nsample) ? L : nsample - 1;   // full: the current largest drops out
+                        while (pos > 0 && list[pos - 1] > k) { list[pos] = list[pos - 1]; --pos; }
+                        list[pos] = k;
+                        if (L < nsample) ++L;
+                        if (L == nsample) last = list[nsample - 1];
+                    }
+                }
+            }
+        }
+        if (serial) {   // the reference's scan: ascending index, stop at nsample hits
+            L = 0;
+            for (int k = 0; k < n; ++k) {
+                const float d2 = sqdist(qx, qy, qz, xyz[(size_t)k * 3], xyz[(size_t)k * 3 + 1], xyz[(size_t)k * 3 + 2]);
+                bool hit = d2 < r2_out;
+                if (MODE == BQ_DILATED) hit = hit && (d2 >= r2_in);
+                if (hit) {
+                    list[L++] = k;
+                    if (L >= nsample) break;
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- rows out, one warp-wide store per 32 slots: hits, then the variant's padding ----
+    const int q_base = blockIdx.x * BQG_QT + (tid & ~31);
+    for (int j = 0; j < 32; ++j) {
+        const int qi = q_base + j;
+        const int c = __shfl_sync(0xffffffffu, L, j);
+        if (qi >= m) break;
+        if (MODE != BQ_PLAIN && lane == 0) idx_cnt[(size_t)bs * m + qi] = c;
+        if (c == 0) continue;   // reference leaves the (pre-zeroed) row untouched
+        const int *src = lists + (size_t)((tid & ~31) + j) * pitch;
+        int *row = idx + ((size_t)bs * m + qi) * nsample;
+        for (int s = lane; s < nsample; s += 32) {
+            int v;
+            if (s < c) v = src[s];
+            else v = (MODE == BQ_PLAIN) ? src[0] : src[s % c];
+            row[s] = v;
+        }
+    }
+}
+
+constexpr int BQG_MIN_N = 2048;   // below this the brute-force kernel is already cheap
+
 template <int MODE>
 static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int nsample, const float *new_xyz,
-                             const float *xyz, int *idx_cnt, int *idx, cudaStream_t s) {
+                             const float *xyz, int *idx_cnt, int *idx, int impl, void *workspace,
+                             size_t workspace_bytes, cudaStream_t s) {
     if (b < 0 || n < 0 || m < 0 || nsample < 0) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: negative size");
     if (b == 0 || m == 0) return DE6D_OK;
     if (!new_xyz || !idx || (n > 0 && !xyz) || (MODE != BQ_PLAIN && !idx_cnt))
         return de6d_set_error(DE6D_ERR_INVALID, "ball_query: null pointer");
     if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: batch > 65535");
-    size_t smem = (size_t)BQ_TILE * 12 + (size_t)BQ_QPB * (nsample > 0 ? nsample : 1) * sizeof(int);
-    if (smem > 200 * 1024) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: nsample too large");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query smem attribute");
-        configured = 200 * 1024;
-    }
     // radius*radius in float, as the reference kernels compute it (ball_query_gpu.cu:29,74-75,114)
     const float r2_in = r_in * r_in, r2_out = r_out * r_out;
+
+    const size_t list_smem = (size_t)BQG_QT * (size_t)((nsample | 1)) * sizeof(int);
+    bool grid_ok = n > 0 && nsample > 0 && list_smem <= 160 * 1024;
+    bool use_grid = grid_ok && (impl == 2 || (impl == 0 && n >= BQG_MIN_N));
+    if (impl == 2 && !grid_ok) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: grid kernel not applicable");
+    if (use_grid) {
+        const size_t per = bqg_ws_per_cloud(n), need = per * (size_t)b;
+        void *ws = workspace;
+        bool own = false;
+        if (!ws) {   // raw C callers without a workspace: stream-ordered scratch
+            cudaError_t e = cudaMallocAsync(&ws, need, s);
+            if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query workspace");
+            own = true;
+        } else if (workspace_bytes < need) {
+            return de6d_set_error(DE6D_ERR_INVALID, "ball_query: workspace too small");
+        }
+        static bool configured[4] = {false, false, false, false};
+        if (!configured[3]) {
+            cudaError_t e = cudaFuncSetAttribute(bq_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_CAP * 4);
+            if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query grid smem attribute");
+            configured[3] = true;
+        }
+        if (!configured[MODE]) {
+            cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query query smem attribute");
+            configured[MODE] = true;
+        }
+        const float r_abs = fabsf(r_out);
+        bq_grid_build_kernel<<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
+        DE6D_CHECK_LAUNCH("bq_grid_build_kernel");
+        double lim = 3.0 * sqrt((double)nsample * (double)n);
+        if (lim < 1024.0) lim = 1024.0;
+        if (lim > 2.0e9) lim = 2.0e9;
+        dim3 grid(ceil_div(m, BQG_QT), b);
+        bq_grid_query_kernel<MODE><<<grid, BQG_QT, list_smem, s>>>(n, m, r_abs, r2_in, r2_out, nsample, (int)lim, new_xyz, xyz,
+                                                                 reinterpret_cast<const unsigned char *>(ws), per, idx_cnt, idx);
+        DE6D_CHECK_LAUNCH("bq_grid_query_kernel");
+        if (own) {
+            cudaError_t e = cudaFreeAsync(ws, s);
+            if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query workspace free");
+        }
+        return DE6D_OK;
+    }
+
+    size_t smem = (size_t)BQ_TILE * 12 + (size_t)BQ_QPB * (nsample > 0 ? nsample : 1) * sizeof(int);
+    if (smem > 200 * 1024) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: nsample too large");
+    static size_t configured_bf = 0;
+    if (smem > 48 * 1024 && smem > configured_bf) {
+        cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query smem attribute");
+        configured_bf = 200 * 1024;
+    }
     dim3 grid(ceil_div(m, BQ_QPB), b);
     ball_query_kernel<MODE><<<grid, BQ_NWARP * 32, smem, s>>>(n, m, r2_in, r2_out, nsample, new_xyz, xyz, idx_cnt, idx);
     DE6D_CHECK_LAUNCH("ball_query_kernel");
@@ -142,14 +447,32 @@ using namespace de6d;
 
 extern "C" int de6d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
                                int *idx, cudaStream_t stream) {
-    return launch_ball_query<BQ_PLAIN>(b, n, m, 0.f, radius, nsample, new_xyz, xyz, nullptr, idx, stream);
+    return launch_ball_query<BQ_PLAIN>(b, n, m, 0.f, radius, nsample, new_xyz, xyz, nullptr, idx, 0, nullptr, 0, stream);
 }
 extern "C" int de6d_ball_query_cnt(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                                    const float *xyz, int *idx_cnt, int *idx, cudaStream_t stream) {
-    return launch_ball_query<BQ_CNT>(b, n, m, 0.f, radius, nsample, new_xyz, xyz, idx_cnt, idx, stream);
+    return launch_ball_query<BQ_CNT>(b, n, m, 0.f, radius, nsample, new_xyz, xyz, idx_cnt, idx, 0, nullptr, 0, stream);
 }
 extern "C" int de6d_ball_query_dilated(int b, int n, int m, float radius_in, float radius_out, int nsample,
                                        const float *new_xyz, const float *xyz, int *idx_cnt, int *idx,
                                        cudaStream_t stream) {
-    return launch_ball_query<BQ_DILATED>(b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, stream);
+    return launch_ball_query<BQ_DILATED>(b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, 0, nullptr, 0, stream);
+}
+
+// Scratch the automatic kernel choice needs for (b, n): 0 when the brute-force kernel will be used.
+extern "C" size_t de6d_ball_query_workspace_bytes(int b, int n) {
+    if (b <= 0 || n < BQG_MIN_N) return 0;
+    return bqg_ws_per_cloud(n) * (size_t)b;
+}
+
+// mode: 0 plain (ball_query), 1 counted (ball_query_cnt), 2 dilated.  impl: 0 auto, 1 brute-force kernel, 2 grid
+// kernel.  workspace: de6d_ball_query_workspace_bytes(b, n) bytes of device scratch, or NULL (the grid path then
+// takes stream-ordered scratch from cudaMallocAsync).
+extern "C" int de6d_ball_query_ex(int mode, int impl, int b, int n, int m, float radius_in, float radius_out, int nsample,
+                                  const float *new_xyz, const float *xyz, int *idx_cnt, int *idx, void *workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+    if (mode == 0) return launch_ball_query<BQ_PLAIN>(b, n, m, 0.f, radius_out, nsample, new_xyz, xyz, nullptr, idx, impl, workspace, workspace_bytes, stream);
+    if (mode == 1) return launch_ball_query<BQ_CNT>(b, n, m, 0.f, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, impl, workspace, workspace_bytes, stream);
+    if (mode == 2) return launch_ball_query<BQ_DILATED>(b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, impl, workspace, workspace_bytes, stream);
+    return de6d_set_error(DE6D_ERR_INVALID, "ball_query_ex: unknown mode");
 }

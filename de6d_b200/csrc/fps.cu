@@ -16,6 +16,7 @@
 //     bucket -> warp -> CTA with ONE __syncthreads per selected point (double-buffered exchange slots).
 #include "common.cuh"
 #include <math.h>
+#include <type_traits>
 
 namespace de6d {
 
@@ -282,16 +283,19 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
                 act = ((lane * NW + w) << 5) < n;
             }
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, act);
-#pragma unroll
-        for (int j = 0; j < BPW; ++j) {
-            if (mask & (1u << j)) {  // warp-uniform
+        unsigned mask = __ballot_sync(0xffffffffu, act);
+        // Visit only the active buckets.  The min-distances live in registers, so the bucket number must be a
+        // compile-time constant inside the body: a warp-uniform switch (one indirect branch per active bucket)
+        // instead of BPW predicated copies of the body that every iteration would have to walk through.
+        auto visit = [&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            if constexpr (j < BPW) {
                 const int p = ((j * NW + w) << 5) | lane;
                 float d = sqdist(sx[p], sy[p], sz[p], x1, y1, z1);
                 float t = fminf(d, temp[j]);
                 if (p >= n) t = -INFINITY;
                 temp[j] = t;
-                float val = MODE == FPS_S ? sfps_key(t, wt[j]) : t;
+                float val = MODE == FPS_S ? sfps_key(t, wt[MODE == FPS_S ? j : 0]) : t;
                 uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
                 uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
                 uint32_t tm;
@@ -299,6 +303,21 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
                 warp_argmax(v, wd);
                 if (MODE == FPS_D) tm = v;
                 if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+            }
+        };
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            switch (j) {
+#define DE6D_FPS_CASE(J) case J: visit(std::integral_constant<int, J>{}); break;
+                DE6D_FPS_CASE(0) DE6D_FPS_CASE(1) DE6D_FPS_CASE(2) DE6D_FPS_CASE(3) DE6D_FPS_CASE(4) DE6D_FPS_CASE(5)
+                DE6D_FPS_CASE(6) DE6D_FPS_CASE(7) DE6D_FPS_CASE(8) DE6D_FPS_CASE(9) DE6D_FPS_CASE(10) DE6D_FPS_CASE(11)
+                DE6D_FPS_CASE(12) DE6D_FPS_CASE(13) DE6D_FPS_CASE(14) DE6D_FPS_CASE(15) DE6D_FPS_CASE(16) DE6D_FPS_CASE(17)
+                DE6D_FPS_CASE(18) DE6D_FPS_CASE(19) DE6D_FPS_CASE(20) DE6D_FPS_CASE(21) DE6D_FPS_CASE(22) DE6D_FPS_CASE(23)
+                DE6D_FPS_CASE(24) DE6D_FPS_CASE(25) DE6D_FPS_CASE(26) DE6D_FPS_CASE(27) DE6D_FPS_CASE(28) DE6D_FPS_CASE(29)
+                DE6D_FPS_CASE(30) DE6D_FPS_CASE(31)
+#undef DE6D_FPS_CASE
+                default: break;
             }
         }
         uint32_t v = bval, wd = bword;

@@ -39,11 +39,24 @@ farthest_point_sample = furthest_point_sample = FarthestPointSampling.apply
 
 @torch.no_grad()
 def calc_dist_matrix_for_sampling(xyz: torch.Tensor, features: torch.Tensor = None, gamma: float = 1.0):
-    """F-FPS input (reference :36-44): pairwise L2 of coordinates plus gamma * pairwise L2 of features."""
-    dist = torch.cdist(xyz, xyz)
+    """F-FPS input (reference :36-44): pairwise L2 of coordinates plus gamma * pairwise L2 of features, (B, N, N).
+    xyz (B, N, 3), features (B, N, C) -- any strides, e.g. the permuted view of a (B, C, N) tensor.  One kernel with
+    direct differences instead of the reference's two torch.cdist (GEMM expansion) + scale + add passes; values
+    agree with torch.cdist to its own rounding error (~1e-3 abs for close points, where the expansion cancels)."""
+    from ._lib import call
+    assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.dim() == 3 and xyz.size(2) == 3
+    xyz = xyz.contiguous()
+    B, N, _ = xyz.shape
+    out = torch.empty((B, N, N), dtype=torch.float32, device=xyz.device)
     if features is not None:
-        dist += torch.cdist(features, features) * gamma
-    return dist
+        assert features.is_cuda and features.dtype == torch.float32 and features.shape[:2] == (B, N)
+        sb, sn, sc = features.stride()
+        call("de6d_dist_matrix", B, N, features.size(2), xyz.data_ptr(), features.data_ptr(), sb, sn, sc, float(gamma),
+             out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    else:
+        call("de6d_dist_matrix", B, N, 0, xyz.data_ptr(), None, 0, 0, 0, float(gamma), out.data_ptr(),
+             torch.cuda.current_stream().cuda_stream)
+    return out
 
 
 @torch.no_grad()

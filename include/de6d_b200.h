@@ -55,6 +55,13 @@ int de6d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *t
 int de6d_furthest_point_sampling_matrix(int b, int n, int m, const float *matrix, float *temp, int *idx,
                                         cudaStream_t stream);
 
+/* calc_dist_matrix_for_sampling(xyz, features, gamma)   pointnet2_utils.py:36-44 (two torch.cdist + scale + add in the
+ * reference): out[b,i,j] = |xyz_i - xyz_j| + gamma * |features_i - features_j|, (b,n,n) f32, one kernel, one write.
+ * xyz (b,n,3); features: element (b,i,ch) at features[b*stride_b + i*stride_n + ch*stride_c] (strides in elements,
+ * so both a (b,n,c) tensor and the permuted view of a (b,c,n) tensor are accepted), or NULL / c == 0 for none. */
+int de6d_dist_matrix(int b, int n, int c, const float *xyz, const float *features, long long stride_b,
+                     long long stride_n, long long stride_c, float gamma, float *out, cudaStream_t stream);
+
 /* furthest_point_sampling_weights_wrapper(b, n, m, xyz, weights, temp, idx)   sampling.cpp:63-73, sampling_gpu.cu:419-585
  * weights (b,n) f32; first index = argmax(weights). */
 int de6d_furthest_point_sampling_weights(int b, int n, int m, const float *xyz, const float *weights, float *temp,
@@ -89,6 +96,16 @@ int de6d_ball_query_cnt(int b, int n, int m, float radius, int nsample, const fl
  * ball_query.cpp:57-67, ball_query_gpu.cu:53-91 */
 int de6d_ball_query_dilated(int b, int n, int m, float radius_in, float radius_out, int nsample, const float *new_xyz,
                             const float *xyz, int *idx_cnt, int *idx, cudaStream_t stream);
+
+/* The three calls above pick a kernel by size: clouds of >= 2048 points go through a per-cloud uniform grid (same
+ * results, see csrc/ball_query.cu) and need device scratch, which they take from cudaMallocAsync on `stream`.
+ * Hosts with their own allocator (the torch layer) use the explicit form instead:
+ *   mode 0 = ball_query, 1 = ball_query_cnt, 2 = ball_query_dilated;  impl 0 = automatic, 1 = brute-force kernel,
+ *   2 = grid kernel;  workspace = de6d_ball_query_workspace_bytes(b, n) bytes (0 = none needed) or NULL. */
+size_t de6d_ball_query_workspace_bytes(int b, int n);
+int de6d_ball_query_ex(int mode, int impl, int b, int n, int m, float radius_in, float radius_out, int nsample,
+                       const float *new_xyz, const float *xyz, int *idx_cnt, int *idx, void *workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- pointnet2_batch: grouping ------------------------------------------------------------------------ */
 

@@ -19,10 +19,12 @@ def _group(xyz, new_xyz, feats, r, ns):
     return cnt, np.concatenate([g_xyz, g_feat], axis=1)
 
 
-def run_chain(cfg, host, frames=None, keep_groups=False, matrices=None):
+def run_chain(cfg, host, frames=None, keep_groups=False, matrices=None, ffps_matrix="oracle"):
     """host: dict of numpy arrays / CPU tensors from de6d_b200.chain.make_inputs.  frames: optional slice.
     matrices: optional {layer index: (B, n, n) array} used instead of recomputing the F-FPS distance matrix
-    (torch.cdist differs in the last bits between CPU and CUDA; the matrix is an input of the op under test)."""
+    (the matrix is an input of the F-FPS op under test).  ffps_matrix: "oracle" = orc.calc_dist_matrix_for_sampling
+    (direct differences, bit-identical to de6d_b200's dist-matrix kernel), "torch" = torch.cdist exactly as the
+    reference's calc_dist_matrix_for_sampling (used by the CPU timing legs of bench.py)."""
     h = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
     if frames is not None:
         h = {k: np.ascontiguousarray(v[frames]) for k, v in h.items()}
@@ -40,8 +42,10 @@ def run_chain(cfg, host, frames=None, keep_groups=False, matrices=None):
                 f = torch.from_numpy(np.ascontiguousarray(feats[:, :, lo:hi])).permute(0, 2, 1)
                 if matrices is not None and li in matrices:
                     mat = torch.from_numpy(np.ascontiguousarray(matrices[li]))
-                else:
+                elif ffps_matrix == "torch":
                     mat = torch.cdist(x, x) + torch.cdist(f, f) * cfg.ffps_gamma
+                else:
+                    mat = torch.from_numpy(orc.calc_dist_matrix_for_sampling(sl, np.ascontiguousarray(f.numpy()), cfg.ffps_gamma))
                 idx = orc.furthest_point_sample_matrix(mat.numpy(), npnt)
             elif method == "s-fps":
                 idx = orc.furthest_point_sample_weights(sl, np.ascontiguousarray(scores[:, lo:hi]), npnt)

@@ -257,6 +257,36 @@ ORC_API void orc_group_points_grad(int b, int c, int n, int npoints, int nsample
         }
 }
 
+/* F-FPS distance matrix: calc_dist_matrix_for_sampling, pointnet2/pointnet2_batch/pointnet2_utils.py:36-44
+ *   dist = cdist(xyz, xyz) + cdist(features, features) * gamma
+ * torch.cdist is a third-party routine (torch 2.11.0; for N > 25 it expands |a|^2+|b|^2-2ab through a GEMM, whose
+ * summation order is not specified), so this is NOT a bitwise restatement of torch: it is the mathematical
+ * definition evaluated with direct differences in a fixed order, which de6d_b200's dist-matrix kernel reproduces
+ * bit for bit.  Against torch.cdist the two agree to ~1e-3 absolute (torch's expansion cancels for close
+ * points); the matrix is an INPUT of the F-FPS kernel under test, so this does not enter index parity.
+ * features: (b, n, c) contiguous or NULL. */
+ORC_API void orc_dist_matrix(int b, int n, int c, const float *xyz, const float *features, float gamma, float *out) {
+    for (int bi = 0; bi < b; ++bi) {
+        const float *x = xyz + (size_t)bi * n * 3;
+        const float *f = features ? features + (size_t)bi * n * c : 0;
+        float *o = out + (size_t)bi * n * n;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                float d1 = sqrtf(sqdist(x[i * 3], x[i * 3 + 1], x[i * 3 + 2], x[j * 3], x[j * 3 + 1], x[j * 3 + 2]));
+                if (f) {
+                    float acc = 0.f;
+                    for (int ch = 0; ch < c; ++ch) {
+                        float t = f[(size_t)i * c + ch] - f[(size_t)j * c + ch];
+                        acc = fmaf(t, t, acc);
+                    }
+                    float g = sqrtf(acc) * gamma;
+                    d1 = d1 + g;
+                }
+                o[(size_t)i * n + j] = d1;
+            }
+    }
+}
+
 /* three_nn: interpolate_gpu.cu:16-59.  Running minima are double there; every value stored in them is a
  * float (or the 1e40 sentinel, which converts to +inf on the final store), so the compares are restated in double. */
 ORC_API void orc_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx) {

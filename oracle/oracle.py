@@ -85,6 +85,19 @@ def furthest_point_sample_weights(xyz, weights, npoint, return_temp=False):
     return (out, temp) if return_temp else out
 
 
+def calc_dist_matrix_for_sampling(xyz, features=None, gamma=1.0):
+    """pointnet2_utils.py:36-44 with direct differences in a fixed order (see orc_dist_matrix).
+    xyz (B, N, 3), features (B, N, C) or None -> (B, N, N)."""
+    xyz = _f32(xyz); B, N, _ = xyz.shape
+    out = np.zeros((B, N, N), np.float32)
+    if features is not None:
+        features = _f32(features); Cc = features.shape[2]
+        lib().orc_dist_matrix(B, N, Cc, _fp(xyz), _fp(features), C.c_float(gamma), _fp(out))
+    else:
+        lib().orc_dist_matrix(B, N, 0, _fp(xyz), None, C.c_float(gamma), _fp(out))
+    return out
+
+
 def gather_operation(features, idx):
     features = _f32(features); idx = _i32(idx)
     B, Cc, N = features.shape; M = idx.shape[1]

@@ -160,3 +160,16 @@ def test_nms_sweep_properties(orc):
     assert iou.max() <= 0.1                       # survivors do not suppress each other
     keep2 = orc.nms_gpu(kept, sc[0][keep], 0.1)   # idempotence
     np.testing.assert_array_equal(np.sort(keep2), np.arange(len(keep)))
+
+
+def test_dist_matrix_against_float64(orc):
+    """orc.calc_dist_matrix_for_sampling (pointnet2_utils.py:36-44 with direct differences) against float64 torch.cdist."""
+    import torch
+    xyz = synth.clouds(2, 150, seed=9, dup_frac=0.1)
+    f = np.ascontiguousarray(synth.features(2, 24, 150, seed=9).transpose(0, 2, 1))
+    got = orc.calc_dist_matrix_for_sampling(xyz, f, 0.5)
+    x64, f64 = torch.from_numpy(xyz).double(), torch.from_numpy(f).double()
+    ref = (torch.cdist(x64, x64) + torch.cdist(f64, f64) * 0.5).numpy()
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-6)
+    np.testing.assert_array_equal(got, got.transpose(0, 2, 1))
+    assert (np.diagonal(got, axis1=1, axis2=2) == 0).all()

@@ -95,6 +95,44 @@ def test_ffps_vs_oracle(orc, ops, B, N, M):
     np.testing.assert_array_equal(got, orc.furthest_point_sample_matrix(mat, M))
 
 
+@pytest.mark.parametrize("B,N,C,layout", [(2, 200, 16, "bnc"), (2, 257, 5, "bcn"), (1, 64, 64, "bcn"), (1, 130, 33, "bnc"),
+                                            (2, 96, 0, "none"), (1, 1, 3, "bnc")])
+def test_dist_matrix_vs_oracle(orc, ops, B, N, C, layout):
+    """calc_dist_matrix_for_sampling: bit-exact against the oracle's direct-difference statement, bitwise symmetric,
+    and equal to torch.cdist within torch's own cancellation error."""
+    pu = ops[0]
+    xyz = synth.clouds(B, N, seed=N, dup_frac=0.1)
+    if layout == "none":
+        got = pu.calc_dist_matrix_for_sampling(cu(xyz), None, 0.5).cpu().numpy()
+        want = orc.calc_dist_matrix_for_sampling(xyz, None, 0.5)
+        ref = torch.cdist(torch.from_numpy(xyz).double(), torch.from_numpy(xyz).double()).numpy()
+    else:
+        feats = synth.features(B, C, N, seed=2)                       # (B, C, N)
+        f_bnc = np.ascontiguousarray(feats.transpose(0, 2, 1))
+        dev_f = cu(f_bnc) if layout == "bnc" else cu(feats).permute(0, 2, 1)   # contiguous, or the reference's permuted view
+        got = pu.calc_dist_matrix_for_sampling(cu(xyz), dev_f, 0.7).cpu().numpy()
+        want = orc.calc_dist_matrix_for_sampling(xyz, f_bnc, 0.7)
+        x64, f64 = torch.from_numpy(xyz).double(), torch.from_numpy(f_bnc).double()
+        ref = (torch.cdist(x64, x64) + torch.cdist(f64, f64) * 0.7).numpy()
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got, got.transpose(0, 2, 1))
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-6)
+
+
+def test_dist_matrix_full_size_properties(ops):
+    """Layer-2 shape (N = 4096, C = 64): symmetric, zero diagonal, agrees with torch.cdist on the device."""
+    pu = ops[0]
+    xyz = cu(synth.clouds(2, 4096, seed=5))
+    f = cu(synth.features(2, 64, 4096, seed=5)).permute(0, 2, 1)
+    got = pu.calc_dist_matrix_for_sampling(xyz, f, 1.0)
+    assert torch.equal(got, got.transpose(1, 2))
+    assert float(got.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+    ref = torch.cdist(xyz, xyz) + torch.cdist(f, f)
+    assert float((got - ref).abs().max()) < 5e-3      # torch's GEMM expansion loses ~1e-3 on close pairs
+    idx = pu.furthest_point_sample_matrix(got, 512)
+    assert all(len(set(r.tolist())) == 512 for r in idx.cpu())
+
+
 def test_fps_full_size_properties(lib, ops):
     """BASELINE size (16 x 16384 -> 4096): pruned kernel == unpruned kernel == generic kernel, indices unique."""
     xyz = synth.clouds(16, 16384, seed=0, dup_frac=0.0)
@@ -115,21 +153,93 @@ def test_fps_full_size_properties(lib, ops):
 
 
 # ------------------------------------------------------------------------------------------------ ball query / group / gather
+def _bq_all(impl, r, ns, x, q, r_in=None):
+    """The three ball-query variants through the compat layer with a pinned kernel choice
+    (0 automatic, 1 brute-force kernel, 2 grid kernel)."""
+    from de6d_b200.compat import pointnet2_batch_cuda as p2
+    B, N, _ = x.shape
+    M = q.shape[1]
+    out = {}
+    idx = torch.zeros((B, M, ns), dtype=torch.int32, device="cuda")
+    p2._ball_query(0, B, N, M, 0.0, r, ns, q, x, None, idx, impl=impl)
+    out["plain"] = idx.cpu().numpy()
+    idx = torch.zeros((B, M, ns), dtype=torch.int32, device="cuda"); cnt = torch.zeros((B, M), dtype=torch.int32, device="cuda")
+    p2._ball_query(1, B, N, M, 0.0, r, ns, q, x, cnt, idx, impl=impl)
+    out["cnt"] = (cnt.cpu().numpy(), idx.cpu().numpy())
+    idx = torch.zeros((B, M, ns), dtype=torch.int32, device="cuda"); cnt = torch.zeros((B, M), dtype=torch.int32, device="cuda")
+    p2._ball_query(2, B, N, M, r * 0.5 if r_in is None else r_in, r, ns, q, x, cnt, idx, impl=impl)
+    out["dil"] = (cnt.cpu().numpy(), idx.cpu().numpy())
+    return out
+
+
+def _bq_check(orc, got, r, ns, xyz, new_xyz):
+    np.testing.assert_array_equal(got["plain"], orc.ball_query(r, ns, xyz, new_xyz))
+    wc, wi = orc.ball_query_cnt(r, ns, xyz, new_xyz)
+    np.testing.assert_array_equal(got["cnt"][0], wc); np.testing.assert_array_equal(got["cnt"][1], wi)
+    wc, wi = orc.ball_query_dilated(r * 0.5, r, ns, xyz, new_xyz)
+    np.testing.assert_array_equal(got["dil"][0], wc); np.testing.assert_array_equal(got["dil"][1], wi)
+
+
 @pytest.mark.parametrize("B,N,M,r,ns", [(2, 1500, 96, 0.5, 16), (2, 1500, 96, 2.0, 16), (1, 4096, 333, 1.0, 32),
-                                        (2, 16384, 512, 0.8, 64), (1, 100, 7, 50.0, 5), (1, 2049, 65, 3.0, 33)])
-def test_ball_query_variants_vs_oracle(orc, ops, B, N, M, r, ns):
-    pu = ops[0]
+                                        (2, 16384, 512, 0.8, 64), (1, 100, 7, 50.0, 5), (1, 2049, 65, 3.0, 33),
+                                        (1, 4096, 300, 30.0, 32), (2, 3000, 257, 0.05, 8)])
+@pytest.mark.parametrize("impl", [0, 1, 2])
+def test_ball_query_variants_vs_oracle(orc, ops, B, N, M, r, ns, impl):
+    """Brute-force kernel, grid kernel (incl. its in-order fallback for balls that swallow the cloud: r = 30, 50) and
+    the automatic choice, all three variants, against the oracle: LiDAR-ring clouds (dense near field: balls
+    overflow nsample), duplicated points, queries far outside the cloud (empty rows)."""
     xyz = synth.lidar_clouds(B, N, seed=N) if N >= 1024 else synth.clouds(B, N, seed=N)
+    xyz[:, 5] = xyz[:, 3]                                   # duplicated points are distinct hits
     new_xyz = np.ascontiguousarray(xyz[:, :: max(N // M, 1)][:, :M]) + np.float32(0.01)
     new_xyz[:, -2:] += 1000.0
-    x, q = cu(xyz), cu(new_xyz)
-    np.testing.assert_array_equal(pu.ball_query(r, ns, x, q).cpu().numpy(), orc.ball_query(r, ns, xyz, new_xyz))
-    cnt, idx = pu.ball_query_cnt(r, ns, x, q)
-    wc, wi = orc.ball_query_cnt(r, ns, xyz, new_xyz)
-    np.testing.assert_array_equal(cnt.cpu().numpy(), wc); np.testing.assert_array_equal(idx.cpu().numpy(), wi)
-    cnt, idx = pu.ball_query_dilated(r * 0.5, r, ns, x, q)
-    wc, wi = orc.ball_query_dilated(r * 0.5, r, ns, xyz, new_xyz)
-    np.testing.assert_array_equal(cnt.cpu().numpy(), wc); np.testing.assert_array_equal(idx.cpu().numpy(), wi)
+    _bq_check(orc, _bq_all(impl, r, ns, cu(xyz), cu(new_xyz)), r, ns, xyz, new_xyz)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_ball_query_radius_boundary_and_degenerate_clouds(orc, impl):
+    """Points placed within a few ulps of the sphere surface (the candidate-set argument of the grid kernel must not
+    lose a point the exact test accepts), a flat cloud (zero extent in z), a single-point cloud, NaN / inf
+    coordinates (never hits; the grid kernel falls back to the in-order scan for that cloud)."""
+    rng = np.random.default_rng(7)
+    N, M, r, ns = 4096, 128, 0.75, 16
+    xyz = synth.clouds(1, N, seed=3)
+    new_xyz = np.ascontiguousarray(xyz[:, :M]) + np.float32(0.3)
+    d = rng.normal(size=(M, 8, 3)); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    scale = r * (1.0 + rng.integers(-4, 5, size=(M, 8, 1)) * 6e-8)
+    xyz[0, 1000:1000 + M * 8] = (new_xyz[0][:, None, :] + d * scale).reshape(-1, 3).astype(np.float32)
+    # axis-aligned offsets of exactly r: the worst case for the cell-range bound
+    xyz[0, 3000:3000 + M] = new_xyz[0] + np.array([r, 0, 0], np.float32)
+    xyz[0, 3200:3200 + M] = new_xyz[0] - np.array([0, np.float32(r) * np.float32(1 - 6e-8), 0], np.float32)
+    _bq_check(orc, _bq_all(impl, r, ns, cu(xyz), cu(new_xyz)), r, ns, xyz, new_xyz)
+    flat = xyz.copy(); flat[..., 2] = 0.5
+    _bq_check(orc, _bq_all(impl, r, ns, cu(flat), cu(new_xyz)), r, ns, flat, new_xyz)
+    one = np.repeat(xyz[:, :1], 2100, axis=1)
+    q1 = np.ascontiguousarray(one[:, :4]) + np.float32(0.1)
+    _bq_check(orc, _bq_all(impl, r, ns, cu(one), cu(q1)), r, ns, one, q1)
+    bad = xyz.copy(); bad[0, 10] = np.nan; bad[0, 11, 0] = np.inf
+    _bq_check(orc, _bq_all(impl, r, ns, cu(bad), cu(new_xyz)), r, ns, bad, new_xyz)
+
+
+def test_ball_query_full_size_grid_equals_brute_force(ops):
+    """BASELINE layer-1 shape (16 x 16384 points, 4096 queries, r in {0.2, 0.4, 0.8}): the grid kernel and the
+    brute-force kernel agree bit for bit on uniform and on LiDAR-ring clouds; rows are ascending up to the count."""
+    pu = ops[0]
+    for maker in (synth.clouds, synth.lidar_clouds):
+        xyz = cu(maker(16, 16384, seed=1))
+        q = pu.gather_operation(xyz.transpose(1, 2).contiguous(), pu.furthest_point_sample(xyz, 4096)).transpose(1, 2).contiguous()
+        for r, ns in ((0.2, 32), (0.4, 32), (0.8, 64)):
+            a, b = _bq_all(1, r, ns, xyz, q), _bq_all(2, r, ns, xyz, q)
+            for k in ("cnt", "dil"):
+                np.testing.assert_array_equal(a[k][0], b[k][0]); np.testing.assert_array_equal(a[k][1], b[k][1])
+            np.testing.assert_array_equal(a["plain"], b["plain"])
+            cnt, idx = b["cnt"]
+            assert (cnt >= 1).all()                       # every query is a cloud point: it finds itself
+            first = np.take_along_axis(idx, np.zeros(idx.shape[:2] + (1,), np.int64), 2)[..., 0]
+            srt = np.sort(idx, axis=2)
+            for bb in range(0, 16, 5):
+                for mm in range(0, 4096, 257):
+                    c = cnt[bb, mm]
+                    assert (np.diff(idx[bb, mm, :c]) > 0).all() and first[bb, mm] == srt[bb, mm, 0]
 
 
 def test_ball_query_leaves_empty_rows_untouched(lib):
@@ -409,8 +519,7 @@ def test_chain_vs_oracle_chain(orc, lib):
     c = chain.OpChain(cfg, 2, use_graph=False, keep_matrices=True)
     c.step_host(host)
     torch.cuda.synchronize()
-    mats = {int(k[1]): v.cpu().numpy() for k, v in c.outputs.items() if k.endswith("_ffps_matrix")}
-    want = chain_ref.run_chain(cfg, host, keep_groups=True, matrices=mats)
+    want = chain_ref.run_chain(cfg, host, keep_groups=True)   # F-FPS matrix from the oracle: bit-identical to the kernel's
     for k, v in want.items():
         if v is None:
             continue
