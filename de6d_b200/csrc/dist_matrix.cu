@@ -4,8 +4,8 @@
 // torch.cdist calls (each a padded SGEMM + clamp + sqrt pass over the (B,N,N) matrix) plus a scale and an add:
 // six full passes over a 64 MB/frame tensor at N = 4096.  Here one kernel produces the final matrix with a single
 // write per element, and only tiles on or above the diagonal are computed -- the value is bitwise symmetric
-// because (a-b)^2 == (b-a)^2 in IEEE arithmetic -- each tile being stored twice (as is and transposed, the
-// transposed copy staged through shared memory so both stores are coalesced 128-bit rows).
+// because (a-b)^2 == (b-a)^2 in IEEE arithmetic -- each tile being stored twice (as is and transposed, both with
+// 128-bit stores).
 //
 // Arithmetic (restated exactly by oracle/de6d_oracle.c:orc_dist_matrix):
 //   d1  = sqrtf(fmaf(dz,dz, fmaf(dx,dx, dy*dy)))                       coordinates, same shape as common.cuh:sqdist
@@ -18,17 +18,17 @@
 
 namespace de6d {
 
-constexpr int DM_TILE = 64;     // outputs per CTA: 64 x 64
-constexpr int DM_CH = 32;       // channels staged per pass
-constexpr int DM_PITCH = DM_TILE + 4;   // keeps float4 rows 16-byte aligned, spreads banks
+constexpr int DM_TILE = 128;    // outputs per CTA: 128 x 128, 8 x 8 per thread (as 2 x 2 blocks of 4 x 4)
+constexpr int DM_CH = 16;       // channels staged per pass
+constexpr int DM_PITCH = DM_TILE + 4;   // keeps float4 rows 16-byte aligned
 
 __global__ void __launch_bounds__(256)
 dist_matrix_kernel(int n, int c, const float *__restrict__ xyz_all, const float *__restrict__ feat_all, long long fsb,
                    long long fsn, long long fsc, float gamma, float *__restrict__ out_all, int vec_ok) {
     __shared__ __align__(16) float fs[2][DM_CH][DM_PITCH];   // [0] rows-tile features, [1] columns-tile features
+    __shared__ float xs[2][3][DM_TILE];
     float(*fa)[DM_PITCH] = fs[0];
     float(*fb)[DM_PITCH] = fs[1];
-    __shared__ float xs[2][3][DM_TILE];
 
     const int tid = threadIdx.x;
     const int T = ceil_div(n, DM_TILE);
@@ -49,17 +49,22 @@ dist_matrix_kernel(int n, int c, const float *__restrict__ xyz_all, const float 
         xs[which][a][p] = gp < n ? xyz[(size_t)gp * 3 + a] : 0.f;
     }
 
-    const int ty = tid >> 4, tx = tid & 15;   // rows i0 + 4*ty .. +3, columns j0 + 4*tx .. +3
-    float acc[4][4];
+    // thread (ty, tx) owns rows {4ty..4ty+3, 64+4ty..} x columns {4tx..4tx+3, 64+4tx..}: every shared-memory read
+    // is a conflict-free 128-bit load, 4 loads feed 128 arithmetic instructions
+    const int ty = tid >> 4, tx = tid & 15;
+    // accumulators as float2 pairs along the column index: the packed-fp32 instructions of sm_100 (FADD2 / FFMA2,
+    // IEEE round-to-nearest per lane, so bit-identical to the scalar form) halve the issue slots of the inner loop.
+    // The column tile is stored NEGATED in shared memory so that a - b is the single packed add a + (-b).
+    float2 acc[8][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+        for (int q = 0; q < 4; ++q) acc[r][q] = make_float2(0.f, 0.f);
 
     if (feat) {
         const bool point_major_fast = fsn <= fsc;   // which index is contiguous in memory: points or channels
         for (int ch0 = 0; ch0 < c; ch0 += DM_CH) {
-            __syncthreads();   // previous pass fully consumed (also orders xs on the first pass)
+            __syncthreads();   // previous pass fully consumed
             for (int e = tid; e < 2 * DM_CH * DM_TILE; e += 256) {
                 const int which = e / (DM_CH * DM_TILE), r = e - which * DM_CH * DM_TILE;
                 int p, ch;
@@ -67,76 +72,77 @@ dist_matrix_kernel(int n, int c, const float *__restrict__ xyz_all, const float 
                 else { p = r / DM_CH; ch = r - p * DM_CH; }
                 const int gp = (which ? j0 : i0) + p, gc = ch0 + ch;
                 const float v = (gp < n && gc < c) ? __ldg(feat + (long long)gp * fsn + (long long)gc * fsc) : 0.f;
-                (which ? fb : fa)[ch][p] = v;
+                if (which) fb[ch][p] = -v; else fa[ch][p] = v;
             }
             __syncthreads();
             const int lim = min(DM_CH, c - ch0);
-#pragma unroll 8
+#pragma unroll 4
             for (int ch = 0; ch < lim; ++ch) {
-                const float4 a4 = *reinterpret_cast<const float4 *>(&fa[ch][ty * 4]);
-                const float4 b4 = *reinterpret_cast<const float4 *>(&fb[ch][tx * 4]);
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                const float4 a0 = *reinterpret_cast<const float4 *>(&fa[ch][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4 *>(&fa[ch][64 + ty * 4]);
+                const float4 b0 = *reinterpret_cast<const float4 *>(&fb[ch][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4 *>(&fb[ch][64 + tx * 4]);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float2 nb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < 8; ++r) {
+                    const float2 a2 = make_float2(av[r], av[r]);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float t = __fsub_rn(av[r], bv[q]);
-                        acc[r][q] = __fmaf_rn(t, t, acc[r][q]);
+                        const float2 t = __fadd2_rn(a2, nb[q]);
+                        acc[r][q] = __ffma2_rn(t, t, acc[r][q]);
                     }
+                }
             }
         }
     }
-    __syncthreads();   // xs visible (no-feature case) / feature tiles free for reuse as the transpose stage
+    __syncthreads();   // xs visible (no-feature case)
 
-    float res[4][4];
+    // ---- epilogue: coordinates term, sqrt, combine; write the tile and (off the diagonal) its transpose ----
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int pi = ty * 4 + r, pj = tx * 4 + q;
-            const float d1 = sqrtf(sqdist(xs[0][0][pi], xs[0][1][pi], xs[0][2][pi], xs[1][0][pj], xs[1][1][pj], xs[1][2][pj]));
-            res[r][q] = feat ? __fadd_rn(d1, __fmul_rn(sqrtf(acc[r][q]), gamma)) : d1;
+        for (int qb = 0; qb < 2; ++qb) {
+            float res[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int pi = rb * 64 + ty * 4 + r, pj = qb * 64 + tx * 4 + q;
+                    const float d1 = sqrtf(sqdist(xs[0][0][pi], xs[0][1][pi], xs[0][2][pi], xs[1][0][pj], xs[1][1][pj], xs[1][2][pj]));
+                    const float2 a2 = acc[rb * 4 + r][qb * 2 + (q >> 1)];
+                    res[r][q] = feat ? __fadd_rn(d1, __fmul_rn(sqrtf((q & 1) ? a2.y : a2.x), gamma)) : d1;
+                }
+            const int gi0 = i0 + rb * 64 + ty * 4, gj0 = j0 + qb * 64 + tx * 4;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {   // rows i, 4 consecutive columns j: 16 lanes cover 256 contiguous bytes
+                const int gi = gi0 + r;
+                if (gi >= n) continue;
+                float *dst = out + (size_t)gi * n + gj0;
+                if (vec_ok && gj0 + 3 < n) {
+                    *reinterpret_cast<float4 *>(dst) = make_float4(res[r][0], res[r][1], res[r][2], res[r][3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (gj0 + q < n) dst[q] = res[r][q];
+                }
+            }
+            if (ti != tj) {                 // transpose: rows j, 4 consecutive columns i (full 32-byte sectors)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gj = gj0 + q;
+                    if (gj >= n) continue;
+                    float *dst = out + (size_t)gj * n + gi0;
+                    if (vec_ok && gi0 + 3 < n) {
+                        *reinterpret_cast<float4 *>(dst) = make_float4(res[0][q], res[1][q], res[2][q], res[3][q]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (gi0 + r < n) dst[r] = res[r][q];
+                    }
+                }
+            }
         }
-
-    // direct tile: rows i, columns j
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int gi = i0 + ty * 4 + r, gj = j0 + tx * 4;
-        if (gi >= n) continue;
-        float *dst = out + (size_t)gi * n + gj;
-        if (vec_ok && gj + 3 < n) {
-            *reinterpret_cast<float4 *>(dst) = make_float4(res[r][0], res[r][1], res[r][2], res[r][3]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (gj + q < n) dst[q] = res[r][q];
-        }
-    }
-    if (ti == tj) return;
-
-    // transposed tile through shared memory (the feature stage is free now: 2 * 32 * 68 floats = 64 * 68)
-    float(*st)[DM_PITCH] = reinterpret_cast<float(*)[DM_PITCH]>(&fs[0][0][0]);
-    static_assert(sizeof(fs) >= sizeof(float) * DM_TILE * DM_PITCH, "transpose stage fits");
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4 *>(&st[tx * 4 + q][ty * 4]) = make_float4(res[0][q], res[1][q], res[2][q], res[3][q]);
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int row = ty + 16 * r;          // 16 threads per row -> 256-byte coalesced stores
-        const int gj = j0 + row, gi = i0 + tx * 4;
-        if (gj >= n) continue;
-        const float4 v = *reinterpret_cast<const float4 *>(&st[row][tx * 4]);
-        float *dst = out + (size_t)gj * n + gi;
-        if (vec_ok && gi + 3 < n) {
-            *reinterpret_cast<float4 *>(dst) = v;
-        } else {
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (gi + q < n) dst[q] = vv[q];
-        }
-    }
 }
 
 }  // namespace de6d

@@ -515,6 +515,11 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, f
     int ibits = 0;
     while (((n - 1) >> log2B) >> ibits) ++ibits;
     const bool prune = impl != 1;
+    if (n <= 16384 && impl == 3 && log2B + ibits <= 14) {   // experimental: twice the warps, half the buckets per warp
+        if (n <= 1024) return launch_bucket<MODE, 16, 2, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+        if (n <= 4096) return launch_bucket<MODE, 32, 4, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+        return launch_bucket<MODE, 32, 16, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+    }
     if (n <= 16384 && impl != 2 && log2B + ibits <= 14) {
         if (n <= 1024)
             return prune ? launch_bucket<MODE, 8, 4, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s)
