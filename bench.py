@@ -58,6 +58,12 @@ def algorithmic_bytes(name, a):
     if name == "de6d_gather_points":
         b, c, n, npnt = a[0], a[1], a[2], a[3]
         return b * (4 * npnt + 8 * c * npnt)
+    if name == "de6d_ball_query_ex":
+        mode, b, n, m, ns = a[0], a[2], a[3], a[4], a[7]
+        return b * (12 * n + 12 * m + 4 * m * ns + (4 * m if mode else 0))
+    if name == "de6d_dist_matrix":
+        b, n, c = a[0], a[1], a[2]
+        return b * (12 * n + 4 * n * c + 4 * n * n)
     if name in ("de6d_ball_query", "de6d_ball_query_cnt"):
         b, n, m, ns = a[0], a[1], a[2], a[4]
         return b * (12 * n + 12 * m + 4 * m * ns + (4 * m if name.endswith("cnt") else 0))
@@ -242,11 +248,18 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     cfg = ch.ChainConfig()
     batch = args.batch
-    host = ch.make_inputs(cfg, batch, seed=rank)
-
-    chain = ch.OpChain(cfg, batch, device=dev)
-    chain.load(host)
-    chain.capture()
+    P = max(1, args.pipeline)
+    # P independent chains (own static buffers, CUDA graph and streams) fed round-robin: step k+1 starts its
+    # latency-bound sampling (one CTA per cloud, 64 of 148 SMs) while step k is in its bandwidth-bound grouping.
+    hosts = [ch.make_inputs(cfg, batch, seed=rank * P + i) for i in range(P)]
+    host = hosts[0]
+    chains = []
+    for i in range(P):
+        c = ch.OpChain(cfg, batch, device=dev)
+        c.load(hosts[i])
+        c.capture()
+        chains.append(c)
+    chain = chains[0]
     torch.cuda.synchronize()
 
     def barrier():
@@ -256,32 +269,40 @@ def run_gpu_arm(args):
 
     out_bytes = sum(v.numel() * v.element_size() for k, v in chain.outputs.items() if isinstance(v, torch.Tensor))
     clocks = ClockSampler(local)
+    tstream = torch.cuda.Stream(dev)
+
+    def timed(step_fn, steps):
+        """K steps over the P chains between two events on a timing stream that fences every chain's stream."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(tstream)
+        for c in chains:
+            c.main.wait_event(e0)
+        for k in range(steps):
+            step_fn(k)
+        for c in chains:
+            ev = torch.cuda.Event()
+            ev.record(c.main)
+            tstream.wait_event(ev)
+        e1.record(tstream)
+        barrier()
+        return e0.elapsed_time(e1)
 
     # ---- device-resident timed region --------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        chain.step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    W = max(args.warmup, 3)
+    timed(lambda k: chains[k % P].step(), W)
     clocks.start()
-    e0.record(chain.main)
-    for _ in range(args.steps):
-        chain.step()
-    e1.record(chain.main)
-    barrier()
-    ms = ddist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms = ddist.max_over_ranks(timed(lambda k: chains[k % P].step(), args.steps), dev)
 
     # ---- end to end: pinned host inputs -> H2D -> chain -> D2H, every step ------------------------------------
-    for _ in range(3):
-        chain.step_host(host)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(chain.main)
-    for _ in range(args.steps):
-        chain.step_host(host, sync=True)
-    f1.record(chain.main)
-    barrier()
+    def e2e_step(k):
+        c = chains[k % P]
+        c.main.synchronize()            # this chain's previous step is complete: its host results are readable
+        c.step_host(hosts[k % P], sync=False)
+
+    timed(e2e_step, 3)
+    ms_e2e = ddist.max_over_ranks(timed(e2e_step, args.steps), dev)
     clocks.stop()
-    ms_e2e = ddist.max_over_ranks(f0.elapsed_time(f1), dev)
     frames_global = batch * world
 
     # ---- per entry-point timing (rank 0): the same chain, one stream, eager, CUDA events around every launch -----
@@ -298,7 +319,12 @@ def run_gpu_arm(args):
         trace = _lib.trace_end()
         agg = {}
         for name, a, t in trace:
-            key = (name, tuple(x for x in a if isinstance(x, int) and not isinstance(x, bool) and abs(x) < (1 << 31))[:6])
+            shape = []
+            for x in a:                      # leading sizes / scalars of the C-ABI call, up to the first pointer
+                if x is None or (isinstance(x, int) and abs(x) >= (1 << 31)):
+                    break
+                shape.append(round(x, 4) if isinstance(x, float) else x)
+            key = (name, tuple(shape))
             d = agg.setdefault(key, {"ms": 0.0, "launches": 0, "bytes": algorithmic_bytes(name, a)})
             d["ms"] += t
             d["launches"] += 1
@@ -339,8 +365,9 @@ def run_gpu_arm(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, batch, world,
-                                      note="L2: per-step working set %.0f MB of inputs+outputs >> 126 MB L2, no explicit flush" % (
-                                          (out_bytes + chain.h2d_bytes()) / 1e6)),
+                                      note="L2: per-step working set %.0f MB of inputs+outputs >> 126 MB L2, no explicit flush; "
+                                           "%d chains in flight (round-robin), every step a full pass over its own batch" % (
+                                          (out_bytes + chain.h2d_bytes()) / 1e6, P)),
             "e2e": {"value": frames_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": chain.h2d_bytes(), "d2h_bytes_per_step": chain.d2h_bytes(),
                     "ms_per_step": ms_e2e / args.steps},
@@ -365,6 +392,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--pipeline", type=int, default=2, help="independent chains in flight (1 = strictly serial steps)")
     ap.add_argument("--impl", default="de6d_b200", choices=["de6d_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

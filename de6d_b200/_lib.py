@@ -31,6 +31,7 @@ PROTOTYPES = {
     "de6d_ball_query_ex": [_i, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _sz, _p],
     "de6d_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_group_points_impl": [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
+    "de6d_group_concat": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "de6d_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
     "de6d_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],

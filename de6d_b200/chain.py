@@ -105,11 +105,12 @@ class OpChain:
     N_SIDE = 4
 
     def __init__(self, cfg: ChainConfig, batch: int, device: Optional[torch.device] = None, use_graph: bool = True,
-                 keep_matrices: bool = False, serial: bool = False):
+                 keep_matrices: bool = False, serial: bool = False, fused_group: bool = True):
         self.cfg, self.batch = cfg, batch
         self.keep_matrices = keep_matrices   # tests: expose the F-FPS distance matrices fed to the kernel
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.use_graph = use_graph
+        self.fused_group = fused_group
         self.main = torch.cuda.Stream(self.device)
         if serial:   # everything on one stream (per-kernel timing pass of bench.py, ncu launch lists)
             self.side = [self.main] * self.N_SIDE
@@ -150,11 +151,14 @@ class OpChain:
             st.wait_event(after)
             with torch.cuda.stream(st):
                 idx_cnt, idx = pu.ball_query_cnt(r, ns, xyz, new_xyz)
-                xyz_t = xyz.transpose(1, 2).contiguous()
-                g_xyz = pu.grouping_operation(xyz_t, idx)
-                g_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
-                g_feat = pu.grouping_operation(feats, idx)
-                new_features = torch.cat([g_xyz, g_feat], dim=1)
+                if self.fused_group:      # QueryWithCntAndGroup's tail as one pass (what pu.QueryWithCntAndGroup runs)
+                    new_features = pu.group_concat(xyz, new_xyz, feats, idx)
+                else:                     # the reference's op-by-op composition (pointnet2_utils.py:410-417)
+                    xyz_t = xyz.transpose(1, 2).contiguous()
+                    g_xyz = pu.grouping_operation(xyz_t, idx)
+                    g_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
+                    g_feat = pu.grouping_operation(feats, idx)
+                    new_features = torch.cat([g_xyz, g_feat], dim=1)
                 outs["%s_s%d_cnt" % (tag, si)] = idx_cnt
                 outs["%s_s%d" % (tag, si)] = new_features
                 ev = torch.cuda.Event()

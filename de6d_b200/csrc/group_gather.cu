@@ -55,7 +55,7 @@ constexpr int GS_THREADS = 512;
 template <bool TMA>
 __global__ void __launch_bounds__(GS_THREADS)
 group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chunk, const float *__restrict__ points,
-                    const int *__restrict__ idx, float *__restrict__ out) {
+                    const int *__restrict__ idx, float *__restrict__ out, long long out_bstride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     float *rows = reinterpret_cast<float *>(smem_raw + 128);
@@ -85,7 +85,7 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
     const long long j0 = (long long)blockIdx.x * chunk;
     const long long j1 = min(ms, j0 + chunk);
     const int *ix = idx + (size_t)bs * ms;
-    float *dst = out + ((size_t)bs * c + c0) * ms;
+    float *dst = out + (size_t)bs * out_bstride + (size_t)c0 * ms;
     // chunk is a multiple of 4 and ms % 4 == 0 is checked by the host for this kernel
     for (long long j = j0 + 4ll * threadIdx.x; j < j1; j += 4ll * GS_THREADS) {
         const int4 k = ldg_stream_int4(ix + j);
@@ -101,12 +101,12 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
 template <int CPT>
 __global__ void __launch_bounds__(256)
 group_direct_kernel(int c, int n, long long ms, int vec, const float *__restrict__ points, const int *__restrict__ idx,
-                    float *__restrict__ out) {
+                    float *__restrict__ out, long long out_bstride) {
     const int bs = blockIdx.z;
     const int c0 = blockIdx.y * CPT;
     const int *ix = idx + (size_t)bs * ms;
     const float *src = points + ((size_t)bs * c + c0) * n;
-    float *dst = out + ((size_t)bs * c + c0) * ms;
+    float *dst = out + (size_t)bs * out_bstride + (size_t)c0 * ms;
     const int ch = min(CPT, c - c0);
     const long long stride = (long long)gridDim.x * blockDim.x;
     if (vec) {
@@ -152,8 +152,48 @@ group_grad_kernel(int c, int n, long long ms, const float *__restrict__ grad_out
     }
 }
 
+// Relative coordinates of the grouped points: out[b, a, j] = xyz[b, idx[b, j], a] - new_xyz[b, j / ns, a], a < 3
+// (pointnet2_utils.py:410-412: grouping_operation on the transposed xyz, then the in-place centre subtraction; the
+// transposed copy of xyz and the separate subtraction pass disappear).  grid (x, 1, B).
+__global__ void __launch_bounds__(256)
+group_xyz_center_kernel(int n, int m, int ns, int vec, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                        const int *__restrict__ idx, float *__restrict__ out, long long out_bstride) {
+    const int bs = blockIdx.z;
+    const long long ms = (long long)m * ns;
+    const int *ix = idx + (size_t)bs * ms;
+    const float *src = xyz + (size_t)bs * n * 3;
+    const float *ctr = new_xyz + (size_t)bs * m * 3;
+    float *dst = out + (size_t)bs * out_bstride;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (vec) {   // ns % 4 == 0: four consecutive slots share their centre
+        for (long long j4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; j4 * 4 < ms; j4 += stride) {
+            const long long j = j4 * 4;
+            const int4 k = ldg_stream_int4(ix + j);
+            const float *cq = ctr + (j / ns) * 3;
+            const int kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float cv = __ldg(cq + a);
+                float4 v;
+                v.x = __fsub_rn(__ldg(src + (size_t)kk[0] * 3 + a), cv);
+                v.y = __fsub_rn(__ldg(src + (size_t)kk[1] * 3 + a), cv);
+                v.z = __fsub_rn(__ldg(src + (size_t)kk[2] * 3 + a), cv);
+                v.w = __fsub_rn(__ldg(src + (size_t)kk[3] * 3 + a), cv);
+                stg_stream_float4(dst + (size_t)a * ms + j, v);
+            }
+        }
+    } else {
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < ms; j += stride) {
+            const int k = ix[j];
+            const float *cq = ctr + (j / ns) * 3;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dst[(size_t)a * ms + j] = __fsub_rn(__ldg(src + (size_t)k * 3 + a), __ldg(cq + a));
+        }
+    }
+}
+
 static int group_forward(int b, int c, int n, long long ms, const float *points, const int *idx, float *out,
-                         int force_impl, cudaStream_t s) {
+                         long long out_bstride, int force_impl, cudaStream_t s) {
     if (b < 0 || c < 0 || n < 0 || ms < 0) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: negative size");
     if (b == 0 || c == 0 || ms == 0) return DE6D_OK;
     if (!points || !idx || !out) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: null pointer");
@@ -194,8 +234,8 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
             configured[t] = 1;
         }
         dim3 grid((unsigned)chunks, cgroups, b);
-        if (tma_ok) group_staged_kernel<true><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out);
-        else group_staged_kernel<false><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out);
+        if (tma_ok) group_staged_kernel<true><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride);
+        else group_staged_kernel<false><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride);
         DE6D_CHECK_LAUNCH("group_staged_kernel");
         return DE6D_OK;
     }
@@ -205,7 +245,7 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
     long long bx = ceil_div_ll(work, 256);
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, ceil_div(c, CPT), b);
-    group_direct_kernel<CPT><<<grid, 256, 0, s>>>(c, n, ms, vec, points, idx, out);
+    group_direct_kernel<CPT><<<grid, 256, 0, s>>>(c, n, ms, vec, points, idx, out, out_bstride);
     DE6D_CHECK_LAUNCH("group_direct_kernel");
     return DE6D_OK;
 }
@@ -231,12 +271,12 @@ using namespace de6d;
 
 extern "C" int de6d_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
                                  float *out, cudaStream_t stream) {
-    return group_forward(b, c, n, (long long)npoints * nsample, points, idx, out, 0, stream);
+    return group_forward(b, c, n, (long long)npoints * nsample, points, idx, out, (long long)c * npoints * nsample, 0, stream);
 }
 // impl: 0 auto, 1 direct-gather kernel, 2 shared-memory staged (TMA) kernel -- identical results
 extern "C" int de6d_group_points_impl(int b, int c, int n, int npoints, int nsample, const float *points,
                                       const int *idx, float *out, int impl, cudaStream_t stream) {
-    return group_forward(b, c, n, (long long)npoints * nsample, points, idx, out, impl, stream);
+    return group_forward(b, c, n, (long long)npoints * nsample, points, idx, out, (long long)c * npoints * nsample, impl, stream);
 }
 extern "C" int de6d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
                                       const int *idx, float *grad_points, cudaStream_t stream) {
@@ -244,9 +284,32 @@ extern "C" int de6d_group_points_grad(int b, int c, int n, int npoints, int nsam
 }
 extern "C" int de6d_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx, float *out,
                                   cudaStream_t stream) {
-    return group_forward(b, c, n, (long long)npoints, points, idx, out, 0, stream);
+    return group_forward(b, c, n, (long long)npoints, points, idx, out, (long long)c * npoints, 0, stream);
 }
 extern "C" int de6d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
                                        float *grad_points, cudaStream_t stream) {
     return group_backward(b, c, n, (long long)npoints, grad_out, idx, grad_points, stream);
+}
+
+// Fused tail of QueryAndGroup / QueryWithCntAndGroup / QueryAndGroupDilated (pointnet2_utils.py:368-387,410-424,449-463)
+// for use_xyz = True: out (b, 3 + c, npoints, nsample) = cat(xyz[idx] - new_xyz, features[idx]) written once, instead of
+// transpose + group + in-place subtract + group + torch.cat (three extra passes over the largest tensor of the network).
+// xyz (b,n,3), new_xyz (b,npoints,3), features (b,c,n) or NULL with c == 0, idx (b,npoints,nsample).
+extern "C" int de6d_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
+                                 const float *features, const int *idx, float *out, cudaStream_t stream) {
+    if (b < 0 || c < 0 || n < 0 || npoints < 0 || nsample < 0) return de6d_set_error(DE6D_ERR_INVALID, "group_concat: negative size");
+    const long long ms = (long long)npoints * nsample;
+    if (b == 0 || ms == 0) return DE6D_OK;
+    if (!xyz || !new_xyz || !idx || !out || (c > 0 && !features)) return de6d_set_error(DE6D_ERR_INVALID, "group_concat: null pointer");
+    if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "group_concat: batch > 65535");
+    const long long bstride = (long long)(3 + c) * ms;
+    const int vec = (nsample % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    long long work = vec ? ms / 4 : ms;
+    long long bx = ceil_div_ll(work, 256);
+    if (bx > 2048) bx = 2048;
+    dim3 grid((unsigned)bx, 1, b);
+    group_xyz_center_kernel<<<grid, 256, 0, stream>>>(n, npoints, nsample, vec, xyz, new_xyz, idx, out, bstride);
+    DE6D_CHECK_LAUNCH("group_xyz_center_kernel");
+    if (c > 0) return group_forward(b, c, n, ms, features, idx, out + 3 * ms, bstride, 0, stream);
+    return DE6D_OK;
 }

@@ -234,8 +234,33 @@ def ball_query_dilated(radius_in: float, radius_out: float, nsample: int, xyz: t
     return idx_cnt, idx
 
 
+def group_concat(xyz, new_xyz, features, idx):
+    """cat(xyz[idx] - new_xyz, features[idx]) -> (B, 3 + C, npoint, nsample) in one kernel pass (no autograd).
+    Bit-identical to the reference composition: copies plus one fp32 subtraction."""
+    from ._lib import call
+    B, N, _ = xyz.shape
+    _, M, ns = idx.shape
+    C = 0 if features is None else features.size(1)
+    out = torch.empty((B, 3 + C, M, ns), dtype=torch.float32, device=xyz.device)
+    for t in (xyz, new_xyz, idx) + (() if features is None else (features,)):
+        assert t.is_cuda and t.is_contiguous()
+    call("de6d_group_concat", B, C, N, M, ns, xyz.data_ptr(), new_xyz.data_ptr(),
+         None if features is None else features.data_ptr(), idx.data_ptr(), out.data_ptr(),
+         torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
 def _assemble(xyz, new_xyz, features, idx, use_xyz):
-    """Shared tail of the three grouper modules (reference :368-387, :410-424, :449-463)."""
+    """Shared tail of the three grouper modules (reference :368-387, :410-424, :449-463).  Inference (nothing
+    requires grad) with use_xyz takes the fused single-pass kernel; otherwise the reference composition, whose
+    autograd graph (grouping_operation backward) is kept as is."""
+    if use_xyz and xyz.dtype == torch.float32 and not _needs_grad(xyz, new_xyz, features) and \
+            (features is None or features.dtype == torch.float32):
+        return group_concat(xyz.contiguous(), new_xyz.contiguous(), None if features is None else features.contiguous(), idx)
     xyz_trans = xyz.transpose(1, 2).contiguous()
     grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
     grouped_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)

@@ -116,6 +116,11 @@ int de6d_group_points(int b, int c, int n, int npoints, int nsample, const float
 /* impl 0 = auto, 1 = direct-gather kernel, 2 = TMA-staged shared-memory kernel (identical results). */
 int de6d_group_points_impl(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx,
                            float *out, int impl, cudaStream_t stream);
+/* Fused tail of QueryAndGroup / QueryWithCntAndGroup / QueryAndGroupDilated with use_xyz (pointnet2_utils.py:368-387,
+ * 410-424, 449-463): out (b, 3+c, npoints, nsample) = cat(xyz[idx] - new_xyz, features[idx]) in one pass.
+ * xyz (b,n,3), new_xyz (b,npoints,3), features (b,c,n) (NULL when c == 0), idx (b,npoints,nsample). */
+int de6d_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
+                      const float *features, const int *idx, float *out, cudaStream_t stream);
 /* group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out, idx, grad_points)   group_points.cpp:18-27, group_points_gpu.cu:14-51 */
 int de6d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
                            float *grad_points, cudaStream_t stream);

@@ -298,6 +298,33 @@ def test_query_and_group_modules(orc, ops):
     assert nf2.shape == (2, 7, 128, 16)
 
 
+@pytest.mark.parametrize("B,C,N,M,ns", [(2, 4, 2048, 128, 16), (2, 0, 1500, 77, 5), (1, 70, 4096, 1024, 32), (1, 1, 16384, 4096, 64),
+                                        (2, 9, 1001, 50, 7)])
+def test_group_concat_fused_equals_composition(orc, ops, B, C, N, M, ns):
+    """de6d_group_concat (one pass) == the reference composition transpose -> group -> subtract -> group -> cat,
+    on the device (op by op through the mirror) and on the CPU (oracle); and the grouper module takes the
+    composition whenever autograd needs it, with identical values and a working backward."""
+    pu = ops[0]
+    rng = np.random.default_rng(N)
+    xyz = synth.clouds(B, N, seed=N); new_xyz = np.ascontiguousarray(xyz[:, :M]) + np.float32(0.05)
+    feats = synth.features(B, C, N, seed=3) if C else None
+    idx = rng.integers(0, N, size=(B, M, ns)).astype(np.int32)
+    got = pu.group_concat(cu(xyz), cu(new_xyz), None if feats is None else cu(feats), cu(idx)).cpu().numpy()
+    gx = orc.grouping_operation(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx) - new_xyz.transpose(0, 2, 1)[..., None]
+    want = gx if feats is None else np.concatenate([gx, orc.grouping_operation(feats, idx)], 1)
+    np.testing.assert_array_equal(got, want)
+    if feats is not None:
+        f = cu(feats).requires_grad_(True)
+        with torch.enable_grad():
+            comp = pu._assemble(cu(xyz), cu(new_xyz), f, cu(idx), True)      # autograd path: op-by-op composition
+            comp.sum().backward()
+        np.testing.assert_array_equal(comp.detach().cpu().numpy(), want)
+        counts = np.zeros((B, N), np.float32)
+        for b in range(B):
+            np.add.at(counts[b], idx[b].reshape(-1), 1.0)
+        np.testing.assert_array_equal(f.grad.cpu().numpy(), np.repeat(counts[:, None, :], C, axis=1))
+
+
 # ------------------------------------------------------------------------------------------------ interpolation
 def test_three_nn_interpolate_vs_oracle(orc, ops):
     pu = ops[0]
@@ -502,6 +529,12 @@ def test_chain_graph_equals_eager_and_shards_concatenate(lib):
     out_e = eager.step_host(host)
     for k in out_g:
         assert torch.equal(out_g[k], out_e[k]), k
+    comp = chain.OpChain(cfg, 4, use_graph=False, fused_group=False)   # the reference's op-by-op grouping tail
+    comp.step_host(host)
+    torch.cuda.synchronize()
+    for k, v in eager.outputs.items():
+        if isinstance(v, torch.Tensor):
+            assert torch.equal(v, comp.outputs[k]), k
     # batch sharding: two half-batches reproduce the full batch bit for bit (ops never mix frames)
     halves = []
     for lo in (0, 2):
