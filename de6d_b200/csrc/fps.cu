@@ -22,6 +22,22 @@ namespace de6d {
 
 enum { FPS_D = 0, FPS_S = 1 };
 
+// Explicit shared-window accesses with a 32-bit address computed once: generic pointers derived from the dynamic
+// shared array otherwise cost an S2R SR_CgaCtaId + LEA (shared-window base) in front of every access of the loop.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
 __device__ __forceinline__ float ord2f(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
@@ -273,6 +289,11 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
     }
 
     // ---------------- main loop: one selected point per iteration ------------------------------------------
+    const uint32_t sx_s = (uint32_t)__cvta_generic_to_shared(sx), sy_s = (uint32_t)__cvta_generic_to_shared(sy),
+                   sz_s = (uint32_t)__cvta_generic_to_shared(sz), wbuf_s = (uint32_t)__cvta_generic_to_shared(wbuf);
+    const uint32_t pos0 = (uint32_t)misc[0];
+    const uint32_t lane_off = (uint32_t)((w << 5) | lane) * 4u;
+    constexpr uint32_t ORD_M1 = 0x407fffffu;   // f2ord(-1.0f)
     for (int it = first_it; it < m; ++it) {
         bool act = false;
         if (lane < BPW) {
@@ -291,7 +312,8 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
             constexpr int j = decltype(jc)::value;
             if constexpr (j < BPW) {
                 const int p = ((j * NW + w) << 5) | lane;
-                float d = sqdist(sx[p], sy[p], sz[p], x1, y1, z1);
+                constexpr uint32_t off = (uint32_t)j * NW * 32u * 4u;
+                float d = sqdist(lds_f32(sx_s + lane_off + off), lds_f32(sy_s + lane_off + off), lds_f32(sz_s + lane_off + off), x1, y1, z1);
                 float t = fminf(d, temp[j]);
                 if (p >= n) t = -INFINITY;
                 temp[j] = t;
@@ -322,17 +344,19 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
         }
         uint32_t v = bval, wd = bword;
         warp_argmax(v, wd);
-        if (lane == 0) wbuf[par * NW + w] = make_uint2(v, wd);
+        if (lane == 0) sts_u32x2(wbuf_s + (uint32_t)(par * NW + w) * 8u, v, wd);
         __syncthreads();
-        uint2 e = lane < NW ? wbuf[par * NW + lane] : make_uint2(0u, 0xffffffffu);
+        uint2 e = make_uint2(0u, 0xffffffffu);
+        if (lane < NW) e = lds_u32x2(wbuf_s + (uint32_t)(par * NW + lane) * 8u);
         par ^= 1;
         v = e.x; wd = e.y;
         warp_argmax(v, wd);
-        int pos, k;
-        if (v != 0u && ord2f(v) > -1.0f) { pos = wd & 0x3fff; k = (int)index_of_cprio(wd >> 14, log2B, ibits); }
-        else { pos = misc[0]; k = 0; }
-        x1 = sx[pos]; y1 = sy[pos]; z1 = sz[pos];
-        if (tid == 0) idxs[it] = k;
+        // reference candidate rule: a value must exceed -1 to be selected (best starts at -1, index 0);
+        // ORD_M1 = f2ord(-1.0f), and NaN keys were mapped to 0
+        const bool found = v > ORD_M1;
+        const uint32_t pos = found ? (wd & 0x3fffu) : pos0;
+        x1 = lds_f32(sx_s + pos * 4u); y1 = lds_f32(sy_s + pos * 4u); z1 = lds_f32(sz_s + pos * 4u);
+        if (tid == 0) idxs[it] = found ? (int)index_of_cprio(wd >> 14, log2B, ibits) : 0;
     }
 
     // ---------------- write the running min-distances back (temp is an in/out tensor of the op) ---------
