@@ -22,6 +22,8 @@ PROTOTYPES = {
     "de6d_furthest_point_sampling_impl": [_i, _i, _i, _p, _p, _p, _i, _p],
     "de6d_furthest_point_sampling_weights_impl": [_i, _i, _i, _p, _p, _p, _p, _i, _p],
     "de6d_dist_matrix": [_i, _i, _i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _f, _p, _p],
+    "de6d_furthest_point_sampling_features_fits": [_i, _i],
+    "de6d_furthest_point_sampling_features": [_i, _i, _i, _i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _f, _p, _p, _p],
     "de6d_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_ball_query": [_i, _i, _i, _f, _i, _p, _p, _p, _p],
@@ -56,7 +58,7 @@ _RESTYPES = {
     "de6d_build_info": C.c_char_p,
     "de6d_launch_count": C.c_longlong,
 }
-_NO_STATUS = set(_RESTYPES) | {"de6d_version"}
+_NO_STATUS = set(_RESTYPES) | {"de6d_version", "de6d_furthest_point_sampling_features_fits"}
 
 _lib = None
 

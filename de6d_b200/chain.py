@@ -105,12 +105,14 @@ class OpChain:
     N_SIDE = 4
 
     def __init__(self, cfg: ChainConfig, batch: int, device: Optional[torch.device] = None, use_graph: bool = True,
-                 keep_matrices: bool = False, serial: bool = False, fused_group: bool = True):
+                 keep_matrices: bool = False, serial: bool = False, fused_group: bool = True,
+                 fused_ffps: bool = True):
         self.cfg, self.batch = cfg, batch
         self.keep_matrices = keep_matrices   # tests: expose the F-FPS distance matrices fed to the kernel
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.use_graph = use_graph
         self.fused_group = fused_group
+        self.fused_ffps = fused_ffps
         self.main = torch.cuda.Stream(self.device)
         if serial:   # everything on one stream (per-kernel timing pass of bench.py, ncu launch lists)
             self.side = [self.main] * self.N_SIDE
@@ -195,10 +197,13 @@ class OpChain:
                             sidx = pu.furthest_point_sample(xyz_slice, npnt)
                         elif method == "f-fps":
                             f_slice = feats[:, :, lo:hi].permute(0, 2, 1)
-                            mat = pu.calc_dist_matrix_for_sampling(xyz_slice, f_slice, cfg.ffps_gamma)
-                            sidx = pu.furthest_point_sample_matrix(mat, npnt)
-                            if self.keep_matrices:
-                                outs["l%d_ffps_matrix" % li] = mat
+                            if self.fused_ffps and not self.keep_matrices:
+                                sidx = pu.furthest_point_sample_features(xyz_slice, f_slice, cfg.ffps_gamma, npnt)
+                            else:   # the reference's call pair (pointnet2_modules.py:383-388)
+                                mat = pu.calc_dist_matrix_for_sampling(xyz_slice, f_slice, cfg.ffps_gamma)
+                                sidx = pu.furthest_point_sample_matrix(mat, npnt)
+                                if self.keep_matrices:
+                                    outs["l%d_ffps_matrix" % li] = mat
                         elif method == "s-fps":
                             w = scores[:, lo:hi].contiguous()   # already sigmoid(score) ** gamma (caller side)
                             sidx = pu.furthest_point_sample_weights(xyz_slice, w, npnt)

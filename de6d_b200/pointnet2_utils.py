@@ -71,6 +71,31 @@ def furthest_point_sample_matrix(matrix: torch.Tensor, npoint: int) -> torch.Ten
 
 
 @torch.no_grad()
+def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, gamma: float, npoint: int) -> torch.Tensor:
+    """F-FPS without the (B, N, N) matrix: identical indices to
+        furthest_point_sample_matrix(calc_dist_matrix_for_sampling(xyz, features, gamma), npoint)
+    (the reference's call pair, pointnet2_modules.py:383-388).  xyz (B, N, 3), features (B, N, C) with any strides.
+    One 8-CTA cluster per cloud evaluates only the selected rows out of distributed shared memory; shapes that do not
+    fit on chip take the two-call form."""
+    from ._lib import call, load
+    assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()
+    B, N, _ = xyz.shape
+    C = 0 if features is None else features.size(2)
+    if not load().de6d_furthest_point_sampling_features_fits(N, C):
+        return furthest_point_sample_matrix(calc_dist_matrix_for_sampling(xyz, features, gamma), npoint)
+    out = _new(xyz, (B, npoint), torch.int32)
+    temp = _new(xyz, (B, N), torch.float32).fill_(1e10)
+    if features is None:
+        fptr, (sb, sn, sc) = None, (0, 0, 0)
+    else:
+        assert features.is_cuda and features.dtype == torch.float32 and features.shape[:2] == (B, N)
+        fptr, (sb, sn, sc) = features.data_ptr(), features.stride()
+    call("de6d_furthest_point_sampling_features", B, N, C, npoint, xyz.data_ptr(), fptr, sb, sn, sc, float(gamma),
+         temp.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+@torch.no_grad()
 def furthest_point_sample_weights(xyz: torch.Tensor, weights: torch.Tensor, npoint: int) -> torch.Tensor:
     """S-FPS (reference :89-109): first pick = argmax(weights), then argmax of min-dist * max(w, 1e-12)."""
     assert xyz.is_contiguous()

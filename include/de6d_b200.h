@@ -62,6 +62,15 @@ int de6d_furthest_point_sampling_matrix(int b, int n, int m, const float *matrix
 int de6d_dist_matrix(int b, int n, int c, const float *xyz, const float *features, long long stride_b,
                      long long stride_n, long long stride_c, float gamma, float *out, cudaStream_t stream);
 
+/* Fused F-FPS: the indices de6d_dist_matrix + de6d_furthest_point_sampling_matrix would give (bit for bit), without the
+ * (b,n,n) matrix: one 8-CTA thread-block cluster per cloud keeps the features in distributed shared memory and
+ * evaluates only the m selected rows (pointnet2_modules.py:383-388 is the call pair this replaces).  features as in
+ * de6d_dist_matrix (element strides).  ..._fits(n, c) == 0: shape does not fit on chip, use the two-call form. */
+int de6d_furthest_point_sampling_features_fits(int n, int c);
+int de6d_furthest_point_sampling_features(int b, int n, int c, int m, const float *xyz, const float *features,
+                                          long long stride_b, long long stride_n, long long stride_c, float gamma,
+                                          float *temp, int *idx, cudaStream_t stream);
+
 /* furthest_point_sampling_weights_wrapper(b, n, m, xyz, weights, temp, idx)   sampling.cpp:63-73, sampling_gpu.cu:419-585
  * weights (b,n) f32; first index = argmax(weights). */
 int de6d_furthest_point_sampling_weights(int b, int n, int m, const float *xyz, const float *weights, float *temp,

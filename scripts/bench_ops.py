@@ -115,3 +115,6 @@ def big_fps():
 print("stress D-FPS B=%d 131072->16384 : %8.3f ms" % (Bs, timeit(big_fps, reps=2, warm=1)))
 q = pu.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
 print("stress ball_query_cnt r=0.2 ns=64 M=16384 : %8.3f ms" % timeit(lambda: pu.ball_query_cnt(0.2, 64, xyz, q), reps=3, warm=1))
+xyz = cu(synth.clouds(B, 4096, seed=1))
+f = cu(synth.features(B, 64, 4096, seed=1)).permute(0, 2, 1)
+print("fused F-FPS B=%d n=4096 c=64 m=512 : %8.3f ms" % (B, timeit(lambda: pu.furthest_point_sample_features(xyz, f, 1.0, 512))))

@@ -135,6 +135,41 @@ def test_dist_matrix_full_size_properties(ops):
     assert all(len(set(r.tolist())) == 512 for r in idx.cpu())
 
 
+@pytest.mark.parametrize("B,N,C,M,layout", [(2, 384, 8, 96, "bnc"), (2, 1000, 16, 120, "bcn"), (1, 4096, 64, 512, "bcn"),
+                                              (3, 4100, 20, 64, "bnc"), (1, 700, 0, 50, "none"), (1, 5, 3, 5, "bnc"),
+                                              (2, 2048, 7, 33, "bcn")])
+def test_fused_ffps_equals_matrix_path_and_oracle(orc, ops, B, N, C, M, layout):
+    """furthest_point_sample_features (cluster kernel, no matrix) == calc_dist_matrix_for_sampling +
+    furthest_point_sample_matrix on the device == the same pair evaluated by the oracle on the CPU; duplicated
+    points (exact ties -> the reference tie rule decides) included."""
+    pu = ops[0]
+    xyz = synth.clouds(B, N, seed=N + 1, dup_frac=0.1)
+    if layout == "none":
+        feats_bnc, dev_f = None, None
+    else:
+        feats = synth.features(B, C, N, seed=4)
+        feats[:, :, 7] = feats[:, :, 3]; xyz[:, 7] = xyz[:, 3]            # a fully duplicated point
+        feats_bnc = np.ascontiguousarray(feats.transpose(0, 2, 1))
+        dev_f = cu(feats_bnc) if layout == "bnc" else cu(feats).permute(0, 2, 1)
+    got = pu.furthest_point_sample_features(cu(xyz), dev_f, 0.7, M).cpu().numpy()
+    two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(cu(xyz), dev_f, 0.7), M).cpu().numpy()
+    np.testing.assert_array_equal(got, two)
+    if N <= 1024:
+        want = orc.furthest_point_sample_matrix(orc.calc_dist_matrix_for_sampling(xyz, feats_bnc, 0.7), M)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_fused_ffps_full_batch(ops):
+    """Layer-2 shape of the chain at batch 16 (more clusters than fit at once: several waves)."""
+    pu = ops[0]
+    xyz = cu(synth.clouds(16, 4096, seed=8))
+    f = cu(synth.features(16, 64, 4096, seed=8)).permute(0, 2, 1)
+    got = pu.furthest_point_sample_features(xyz, f, 1.0, 512)
+    two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(xyz, f, 1.0), 512)
+    assert torch.equal(got, two)
+    assert all(len(set(r.tolist())) == 512 for r in got.cpu())
+
+
 def test_fps_full_size_properties(lib, ops):
     """BASELINE size (16 x 16384 -> 4096): pruned kernel == unpruned kernel == generic kernel, indices unique."""
     xyz = synth.clouds(16, 16384, seed=0, dup_frac=0.0)
@@ -529,7 +564,7 @@ def test_chain_graph_equals_eager_and_shards_concatenate(lib):
     out_e = eager.step_host(host)
     for k in out_g:
         assert torch.equal(out_g[k], out_e[k]), k
-    comp = chain.OpChain(cfg, 4, use_graph=False, fused_group=False)   # the reference's op-by-op grouping tail
+    comp = chain.OpChain(cfg, 4, use_graph=False, fused_group=False, fused_ffps=False)   # the reference's op-by-op call sequence
     comp.step_host(host)
     torch.cuda.synchronize()
     for k, v in eager.outputs.items():
