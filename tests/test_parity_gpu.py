@@ -137,7 +137,7 @@ def test_dist_matrix_full_size_properties(ops):
 
 @pytest.mark.parametrize("B,N,C,M,layout", [(2, 384, 8, 96, "bnc"), (2, 1000, 16, 120, "bcn"), (1, 4096, 64, 512, "bcn"),
                                               (3, 4100, 20, 64, "bnc"), (1, 700, 0, 50, "none"), (1, 9, 3, 9, "bnc"),
-                                              (2, 2048, 7, 33, "bcn")])
+                                              (2, 2048, 7, 33, "bcn"), (2, 3000, 32, 100, "bcn"), (1, 4096, 64, 40, "bnc")])
 def test_fused_ffps_equals_matrix_path_and_oracle(orc, ops, B, N, C, M, layout):
     """furthest_point_sample_features (cluster kernel, no matrix) == calc_dist_matrix_for_sampling +
     furthest_point_sample_matrix on the device == the same pair evaluated by the oracle on the CPU; duplicated
