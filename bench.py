@@ -44,6 +44,22 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(entry, shape):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel behind a C-ABI entry point,
+    from the committed `ncu --set full` captures (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the
+    .ncu-rep of the same workload); None when that shape was not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        with open(p) as f:
+            tab = json.load(f)
+    except Exception:
+        return None
+    rec = tab.get(entry + ":" + ",".join(str(x) for x in shape))
+    return None if rec is None else rec.get("dram_bytes")
+
+
 def algorithmic_bytes(name, a):
     """Compulsory HBM bytes of one launch (DESIGN.md 'Algorithmic bytes'), from the C-ABI arguments."""
     if name in ("de6d_furthest_point_sampling", "de6d_furthest_point_sampling_impl"):
@@ -55,6 +71,9 @@ def algorithmic_bytes(name, a):
     if name == "de6d_furthest_point_sampling_matrix":
         b, n, m = a[0], a[1], a[2]
         return b * (4 * n * m + 4 * m)
+    if name == "de6d_furthest_point_sampling_features":
+        b, n, c, m = a[0], a[1], a[2], a[3]
+        return b * (12 * n + 4 * n * c + 4 * m)
     if name == "de6d_gather_points":
         b, c, n, npnt = a[0], a[1], a[2], a[3]
         return b * (4 * npnt + 8 * c * npnt)
@@ -308,6 +327,19 @@ def run_gpu_arm(args):
     ms_e2e = ddist.max_over_ranks(timed(e2e_step, args.steps), dev)
     clocks.stop()
     frames_global = batch * world
+    # the one collective of the deployment: all ranks' padded keep lists gathered over NCCL (outside the timed regions)
+    gather_ms = None
+    if world > 1:
+        keep, num = chain.outputs["nms_keep"], chain.outputs["nms_num"]
+        ddist.gather_detections(keep, num)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        keep_all, num_all = ddist.gather_detections(keep, num)
+        g1.record()
+        torch.cuda.synchronize()
+        assert keep_all.shape[0] == world * batch and num_all.shape[0] == world * batch
+        gather_ms = g0.elapsed_time(g1)
 
     # ---- per entry-point timing (rank 0): the same chain, one stream, eager, CUDA events around every launch -----
     kernels, roofline, fps_us = [], None, None
@@ -346,7 +378,7 @@ def run_gpu_arm(args):
         total_ms = sum(by_name.values())
         top = kernels[0]
         roofline = {"kernel": top["entry"], "shape": top["shape"], "bound": "hbm", "achieved": top["gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": ncu_traffic(top["entry"], top["shape"]), "peak_source": peak_src,
                     "ms_per_launch": top["ms_per_launch"],
                     "share_of_step": round(top["ms_per_launch"] * top["launches_per_step"] / total_ms, 4) if total_ms else None,
                     "note": "dominant entry point by time; timed alone (single stream, eager) with CUDA events on its stream"}
@@ -354,7 +386,8 @@ def run_gpu_arm(args):
             if k["entry"] in ("de6d_group_points", "de6d_group_concat"):
                 if "group_points" not in roofline or k["alg_bytes"] > roofline["group_points"]["alg_bytes"]:
                     roofline["group_points"] = {"entry": k["entry"], "shape": k["shape"], "alg_bytes": k["alg_bytes"], "achieved": k["gbs"],
-                                                "frac": k["frac_hbm"], "ms_per_launch": k["ms_per_launch"]}
+                                                "frac": k["frac_hbm"], "ms_per_launch": k["ms_per_launch"],
+                                                "traffic": ncu_traffic(k["entry"], k["shape"])}
             if k["entry"] == "de6d_furthest_point_sampling" and k["shape"][1] == cfg.n_points:
                 fps_us = 1e3 * k["ms_per_launch"] / batch
         del prof
@@ -383,6 +416,7 @@ def run_gpu_arm(args):
             "fps_us_per_frame": fps_us,
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "detections_all_gather_ms": gather_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -14,6 +14,21 @@ host = ch.make_inputs(cfg, batch, seed=0)
 op = ch.OpChain(cfg, batch, use_graph=False, serial=True)
 op.load(host)
 op.capture()
+if os.environ.get("DE6D_TRACE"):   # entry-point sequence of one step, for scripts/ncu_traffic.py
+    import json
+    from de6d_b200 import _lib
+    _lib.trace_begin()
+    op.step()
+    tr = _lib.trace_end()
+    seq = []
+    for name, a, _ in tr:
+        shape = []
+        for x in a:
+            if x is None or (isinstance(x, int) and abs(x) >= (1 << 31)):
+                break
+            shape.append(round(x, 4) if isinstance(x, float) else x)
+        seq.append([name, shape])
+    json.dump(seq, open(os.environ["DE6D_TRACE"], "w"))
 for _ in range(steps):
     op.step()
 torch.cuda.synchronize()
