@@ -15,6 +15,7 @@
 //   * the per-iteration arg-max is REDUX (redux.sync) on order-preserving integer images of the floats:
 //     bucket -> warp -> CTA with ONE __syncthreads per selected point (double-buffered exchange slots).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <math.h>
 #include <type_traits>
 
@@ -36,6 +37,32 @@ __device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
 }
 __device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
+// ---- thread-block-cluster exchange (clouds larger than one SM: one CTA per 16384-point slice) ----------------
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void fps_st_async(uint32_t remote_addr, uint32_t v, uint32_t remote_mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void fps_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fps_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ float ord2f(uint32_t u) {
@@ -82,14 +109,28 @@ __device__ __forceinline__ float bucket_lower_bound(float lox, float hix, float 
     return __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
 }
 
-template <int MODE, int NW, int BPW, bool PRUNE>
+// CL = true: the cloud is split over the CTAs of a thread-block cluster, CAP points each (n_in up to 8 * 16384).  Every
+// CTA runs the same bucket machinery on its slice; per sample the CTAs exchange one 5-word candidate row (value,
+// global priority, x, y, z) with remote stores that complete on a transaction mbarrier of the destination CTA, and
+// every CTA picks the winner locally -- the selected point's coordinates arrive with the row.
+template <int MODE, int NW, int BPW, bool PRUNE, bool CL = false>
 __global__ void __launch_bounds__(NW * 32, 1)
-fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ xyz_all,
+fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict__ xyz_all,
                   const float *__restrict__ w_all, float *__restrict__ temp_all, int *__restrict__ idx_all) {
     constexpr int T = NW * 32;
     constexpr int CAP = NW * BPW * 32;
     static_assert(BPW <= 32, "one owner lane per bucket");
+    static_assert(!CL || MODE == FPS_D, "the cluster variant covers D-FPS");
     if (m <= 0) return;
+    int rank = 0, S = 1, cloud = blockIdx.x;
+    if (CL) {
+        cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+        rank = (int)cluster.block_rank();
+        S = (int)cluster.num_blocks();
+        cloud = blockIdx.x / S;
+    }
+    const int lo = rank * CAP;                                  // first point of this CTA's slice
+    const int n = CL ? min(max(n_in - lo, 0), CAP) : n_in;      // points this CTA owns
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sx = reinterpret_cast<float *>(smem_raw);
@@ -98,13 +139,16 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
     uint2 *wbuf = reinterpret_cast<uint2 *>(sz + CAP);            // [2][NW]
     float *red = reinterpret_cast<float *>(wbuf + 2 * NW);        // [6][NW] prologue reductions
     int *misc = reinterpret_cast<int *>(red + 6 * NW);            // [0]=pos of index 0, [1]=non-finite flag
+    uint32_t *rows = reinterpret_cast<uint32_t *>(misc + 4);      // CL: [2][8][8] candidate rows of the cluster
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(rows + 2 * 8 * 8);   // CL: [2]
     unsigned long long *sortbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // aliases sx/sy
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
-    const float *wts = MODE == FPS_S ? w_all + (size_t)blockIdx.x * n : nullptr;
-    float *temp_g = temp_all + (size_t)blockIdx.x * n;
-    int *idxs = idx_all + (size_t)blockIdx.x * m;
+    const float *xyz_cloud = xyz_all + (size_t)cloud * n_in * 3;
+    const float *xyz = xyz_cloud + (size_t)lo * 3;
+    const float *wts = MODE == FPS_S ? w_all + (size_t)cloud * n_in : nullptr;
+    float *temp_g = temp_all + (size_t)cloud * n_in + lo;
+    int *idxs = idx_all + (size_t)cloud * m;
 
     if (tid < 2) misc[tid] = 0;
     __syncthreads();
@@ -243,10 +287,17 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
     float x1, y1, z1;
     int first_it;
     __syncthreads();  // smem coordinates + misc[0] visible
+    float gx0 = 0.f, gy0 = 0.f, gz0 = 0.f;   // CL: coordinates of global point 0 (first sample and "nothing found" fallback)
     if (MODE == FPS_D) {
-        const int p0 = misc[0];
-        x1 = sx[p0]; y1 = sy[p0]; z1 = sz[p0];
-        if (tid == 0) idxs[0] = 0;
+        if (CL) {
+            gx0 = xyz_cloud[0]; gy0 = xyz_cloud[1]; gz0 = xyz_cloud[2];
+            x1 = gx0; y1 = gy0; z1 = gz0;
+            if (rank == 0 && tid == 0) idxs[0] = 0;
+        } else {
+            const int p0 = misc[0];
+            x1 = sx[p0]; y1 = sy[p0]; z1 = sz[p0];
+            if (tid == 0) idxs[0] = 0;
+        }
         first_it = 1;
     } else {
         uint32_t v = 0, wd = 0xffffffffu;
@@ -294,6 +345,16 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
     const uint32_t pos0 = (uint32_t)misc[0];
     const uint32_t lane_off = (uint32_t)((w << 5) | lane) * 4u;
     constexpr uint32_t ORD_M1 = 0x407fffffu;   // f2ord(-1.0f)
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows), mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+    uint32_t phases = 0u;
+    if (CL) {
+        if (tid == 0) {
+            fps_mbar_init(mbar_s, 1);
+            fps_mbar_init(mbar_s + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cooperative_groups::this_cluster().sync();   // every CTA of the cluster runs and has its barriers initialised
+    }
     for (int it = first_it; it < m; ++it) {
         bool act = false;
         if (lane < BPW) {
@@ -356,7 +417,44 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
         const bool found = v > ORD_M1;
         const uint32_t pos = found ? (wd & 0x3fffu) : pos0;
         x1 = lds_f32(sx_s + pos * 4u); y1 = lds_f32(sy_s + pos * 4u); z1 = lds_f32(sz_s + pos * 4u);
-        if (tid == 0) idxs[it] = found ? (int)index_of_cprio(wd >> 14, log2B, ibits) : 0;
+        if (!CL) {
+            if (tid == 0) idxs[it] = found ? (int)index_of_cprio(wd >> 14, log2B, ibits) : 0;
+        } else {
+            // this CTA's candidate -> every CTA of the cluster; global priority = (bit-reversed slot, k / B) with the
+            // slice offset added to the k / B field (the slice start is a multiple of B, so the slot is unchanged)
+            const uint32_t cp = wd >> 14;
+            const uint32_t gprio = found ? (((cp >> ibits) << 22) | ((cp & ((1u << ibits) - 1u)) + (uint32_t)(lo >> log2B))) : 0xffffffffu;
+            const uint32_t gv = found ? v : 0u;
+            const int rpar = (it - first_it) & 1;
+            if (tid == 0) fps_mbar_expect_tx(mbar_s + 8u * rpar, (uint32_t)S * 20u);
+            if (w == 0 && lane < S) {
+                const uint32_t row = fps_mapa(rows_s + (uint32_t)((rpar * 8 + rank) * 8) * 4u, (uint32_t)lane);
+                const uint32_t rbar = fps_mapa(mbar_s + 8u * rpar, (uint32_t)lane);
+                fps_st_async(row, gv, rbar);
+                fps_st_async(row + 4u, gprio, rbar);
+                fps_st_async(row + 8u, __float_as_uint(x1), rbar);
+                fps_st_async(row + 12u, __float_as_uint(y1), rbar);
+                fps_st_async(row + 16u, __float_as_uint(z1), rbar);
+            }
+            fps_mbar_wait(mbar_s + 8u * rpar, (phases >> rpar) & 1u);
+            phases ^= 1u << rpar;
+            uint32_t rv = 0u, rp = 0xffffffffu;
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            if (lane < S) {
+                const uint32_t *r = rows + (rpar * 8 + lane) * 8;
+                rv = r[0]; rp = r[1]; rx = __uint_as_float(r[2]); ry = __uint_as_float(r[3]); rz = __uint_as_float(r[4]);
+            }
+            uint32_t bv2 = rv, bp2 = rp;
+            warp_argmax(bv2, bp2);
+            if (bv2 > ORD_M1) {
+                const int src = __ffs(__ballot_sync(0xffffffffu, rv == bv2 && rp == bp2)) - 1;
+                x1 = __shfl_sync(0xffffffffu, rx, src); y1 = __shfl_sync(0xffffffffu, ry, src); z1 = __shfl_sync(0xffffffffu, rz, src);
+                if (rank == 0 && tid == 0) idxs[it] = (int)fps_prio_to_index(bp2, (uint32_t)log2B);
+            } else {   // the reference falls back to index 0 when no value exceeds -1
+                x1 = gx0; y1 = gy0; z1 = gz0;
+                if (rank == 0 && tid == 0) idxs[it] = 0;
+            }
+        }
     }
 
     // ---------------- write the running min-distances back (temp is an in/out tensor of the op) ---------
@@ -368,6 +466,7 @@ fps_bucket_kernel(int n, int m, int log2B, int ibits, const float *__restrict__ 
             temp_g[index_of_cprio(cp, log2B, ibits)] = temp[j];
         }
     }
+    if (CL) cooperative_groups::this_cluster().sync();   // no CTA exits while a peer may still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -515,7 +614,7 @@ template <int MODE, int NW, int BPW, bool PRUNE>
 static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float *xyz, const float *w, float *temp,
                          int *idx, cudaStream_t s) {
     constexpr int CAP = NW * BPW * 32;
-    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16;
+    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16;
     static bool configured = false;  // attribute is per-function, set once per process (idempotent, race-benign)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<MODE, NW, BPW, PRUNE>,
@@ -525,6 +624,37 @@ static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float 
     }
     fps_bucket_kernel<MODE, NW, BPW, PRUNE><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
     DE6D_CHECK_LAUNCH("fps_bucket_kernel");
+    return DE6D_OK;
+}
+
+// D-FPS of clouds larger than one SM's shared memory: a cluster of ceil(n / 16384) <= 8 CTAs per cloud.
+static int launch_bucket_cluster(int b, int n, int m, const float *xyz, float *temp, int *idx, cudaStream_t s) {
+    constexpr int NW = 16, BPW = 32, CAP = NW * BPW * 32;
+    const int S = (n + CAP - 1) / CAP;
+    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16;
+    auto kern = fps_bucket_kernel<FPS_D, NW, BPW, true, true>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return de6d_set_cuda_error(e, "fps cluster smem attribute");
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(S * b));
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float *w = nullptr;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, 10, 4, xyz, w, temp, idx);
+    if (e != cudaSuccess) return de6d_set_cuda_error(e, "fps_bucket_kernel (cluster)");
+    DE6D_CHECK_LAUNCH("fps_bucket_kernel (cluster)");
     return DE6D_OK;
 }
 
@@ -554,6 +684,7 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, f
         return prune ? launch_bucket<MODE, 16, 32, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s)
                      : launch_bucket<MODE, 16, 32, false>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
     }
+    if (MODE == FPS_D && n > 16384 && n <= 8 * 16384 && impl != 2) return launch_bucket_cluster(b, n, m, xyz, temp, idx, s);
     fps_global_kernel<MODE, 1024><<<b, 1024, 0, s>>>(n, m, log2B, xyz, w, temp, idx);
     DE6D_CHECK_LAUNCH("fps_global_kernel");
     return DE6D_OK;

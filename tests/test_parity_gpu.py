@@ -78,6 +78,30 @@ def test_sfps_vs_oracle(orc, lib, B, N, M, impl):
     np.testing.assert_array_equal(got_temp, want_temp)
 
 
+@pytest.mark.parametrize("B,N,M,dup", [(2, 16385, 70, 0.1), (1, 40000, 300, 0.2), (2, 131072, 200, 0.05), (1, 100000, 64, 0.0)])
+def test_dfps_cluster_large_clouds(orc, lib, B, N, M, dup):
+    """Clouds larger than one SM (BASELINE configs[4]: 131072 points): thread-block-cluster kernel (one CTA per
+    16384-point slice, candidates exchanged through distributed shared memory) == generic kernel == oracle,
+    indices and the written-back min-distances."""
+    xyz = synth.lidar_clouds(B, N, seed=N, beams=64) if N % 64 == 0 else synth.clouds(B, N, seed=N, dup_frac=dup)
+    if N % 64 == 0:
+        xyz[:, 17000] = xyz[:, 5]; xyz[:, N - 1] = xyz[:, 16384]     # exact ties across CTA slices
+    want, wtemp = orc.furthest_point_sample(xyz, M, return_temp=True)
+    for impl in (0, 2):
+        idx, temp = _fps_impl(xyz, M, impl)
+        np.testing.assert_array_equal(idx, want)
+        np.testing.assert_array_equal(temp, wtemp)
+
+
+def test_dfps_cluster_stress_shape(lib):
+    """131072 -> 16384 (the stress config): cluster kernel == generic kernel."""
+    xyz = synth.lidar_clouds(1, 131072, seed=9)
+    a, ta = _fps_impl(xyz, 16384, 0)
+    b, tb = _fps_impl(xyz, 16384, 2)
+    np.testing.assert_array_equal(a, b); np.testing.assert_array_equal(ta, tb)
+    assert len(set(a[0].tolist())) == 16384
+
+
 def test_dfps_all_points_identical_and_caller_temp(orc, lib, ops):
     # every distance ties at 0: the tie rule alone decides
     xyz = np.ones((1, 777, 3), np.float32)
