@@ -134,6 +134,8 @@ ball_query_kernel(int n, int m, float r2_in, float r2_out, int nsample, const fl
 // exit, inside the same kernel.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int BQG_CAP = 32768;          // max cells per cloud (128 KB histogram in shared memory)
+constexpr int BQG_CAP_BIG = 1 << 21;    // clouds of more than BQG_BIG_N points: histogram in global memory, finer cells
+constexpr int BQG_BIG_N = 32768;
 constexpr int BQG_BUILD_T = 1024;
 constexpr int BQG_QT = 256;
 
@@ -142,8 +144,11 @@ struct BQGridHeader {
     int dimx, dimy, dimz, valid;
 };
 
+// workspace of one cloud: header | cell_start[cap + 4] | sorted float4[n]
+__host__ __device__ inline int bqg_cap(int n) { return n > BQG_BIG_N ? BQG_CAP_BIG : BQG_CAP; }
+__host__ __device__ inline size_t bqg_sorted_off(int n) { return sizeof(BQGridHeader) + sizeof(int) * (size_t)(bqg_cap(n) + 4); }
 __host__ __device__ inline size_t bqg_ws_per_cloud(int n) {
-    size_t bytes = sizeof(BQGridHeader) + sizeof(int) * (size_t)(BQG_CAP + 4) + 16 * (size_t)n;
+    size_t bytes = bqg_sorted_off(n) + 16 * (size_t)n;
     return (bytes + 255) & ~(size_t)255;
 }
 
@@ -152,11 +157,16 @@ __device__ __forceinline__ int bqg_cell(float v, float o, float inv_c, int dim) 
     return min(max(c, 0), dim - 1);
 }
 
+// BIG = false: histogram / cursors in shared memory (<= BQG_CAP cells).  BIG = true: in the workspace itself
+// (<= BQG_CAP_BIG cells): counts -> inclusive scan in place (tiles of 4096 with a running carry) -> scatter from the
+// END of each cell with atomicSub, which leaves exactly the cell starts behind.
+template <bool BIG>
 __global__ void __launch_bounds__(BQG_BUILD_T)
 bq_grid_build_kernel(int n, float r_abs, const float *__restrict__ xyz_all, unsigned char *__restrict__ ws_all,
                      size_t ws_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *cnt = reinterpret_cast<int *>(smem_raw);            // [BQG_CAP] histogram, then scatter cursors
+    int *cnt = reinterpret_cast<int *>(smem_raw);            // [BQG_CAP] histogram, then scatter cursors (!BIG)
+    constexpr int CAP = BIG ? BQG_CAP_BIG : BQG_CAP;
     __shared__ float red[6][BQG_BUILD_T / 32];
     __shared__ int wsum[BQG_BUILD_T / 32];
     __shared__ BQGridHeader sh;
@@ -166,7 +176,7 @@ bq_grid_build_kernel(int n, float r_abs, const float *__restrict__ xyz_all, unsi
     unsigned char *ws = ws_all + (size_t)blockIdx.x * ws_stride;
     BQGridHeader *hdr = reinterpret_cast<BQGridHeader *>(ws);
     int *cell_start = reinterpret_cast<int *>(ws + sizeof(BQGridHeader));
-    float4 *sorted = reinterpret_cast<float4 *>(ws + sizeof(BQGridHeader) + sizeof(int) * (size_t)(BQG_CAP + 4));
+    float4 *sorted = reinterpret_cast<float4 *>(ws + sizeof(BQGridHeader) + sizeof(int) * (size_t)(CAP + 4));
 
     // ---- bounding box ----
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -207,12 +217,12 @@ bq_grid_build_kernel(int n, float r_abs, const float *__restrict__ xyz_all, unsi
                 const float fx = e[0] / c, fy = e[1] / c, fz = e[2] / c;
                 if (fx < 30000.f && fy < 30000.f && fz < 30000.f) {
                     dx = (int)fx + 1; dy = (int)fy + 1; dz = (int)fz + 1;
-                    if ((long long)dx * dy * dz <= BQG_CAP) break;
+                    if ((long long)dx * dy * dz <= CAP) break;
                 }
                 c *= 1.2f;
                 dx = dy = dz = 1;
             }
-            if ((long long)dx * dy * dz > BQG_CAP) { dx = dy = dz = 1; }
+            if ((long long)dx * dy * dz > CAP) { dx = dy = dz = 1; }
         }
         h.ox = l[0]; h.oy = l[1]; h.oz = l[2];
         h.inv_c = 1.0f / c;
@@ -224,6 +234,62 @@ bq_grid_build_kernel(int n, float r_abs, const float *__restrict__ xyz_all, unsi
     const BQGridHeader h = sh;
     if (!h.valid) return;
     const int ncell = h.dimx * h.dimy * h.dimz;
+
+    if (BIG) {
+        // ---- histogram in the workspace (global atomics; this CTA is the only writer, reads go past L1) ----
+        const int n4 = (ncell + 4) & ~3;   // cells + the closing entry, rounded up to whole int4
+        for (int i = tid * 4; i < n4; i += BQG_BUILD_T * 4) *reinterpret_cast<int4 *>(cell_start + i) = make_int4(0, 0, 0, 0);
+        __syncthreads();
+        for (int k = tid; k < n; k += BQG_BUILD_T) {
+            const float x = xyz[(size_t)k * 3], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
+            const int c = (bqg_cell(z, h.oz, h.inv_c, h.dimz) * h.dimy + bqg_cell(y, h.oy, h.inv_c, h.dimy)) * h.dimx +
+                          bqg_cell(x, h.ox, h.inv_c, h.dimx);
+            atomicAdd(cell_start + c, 1);
+        }
+        __threadfence();
+        __syncthreads();
+        // ---- inclusive scan in place: cell_start[c] = end of cell c ----
+        int carry = 0;
+        for (int base = 0; base < n4; base += BQG_BUILD_T * 4) {
+            const int i = base + tid * 4;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (i < n4) v = __ldcg(reinterpret_cast<const int4 *>(cell_start + i));
+            v.y += v.x; v.z += v.y; v.w += v.z;
+            int incl = v.w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            __syncthreads();   // wsum of the previous tile fully consumed
+            if (lane == 31) wsum[w] = incl;
+            __syncthreads();
+            if (w == 0) {
+                int t2 = wsum[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, t2, o);
+                    if (lane >= o) t2 += t;
+                }
+                wsum[lane] = t2;
+            }
+            __syncthreads();
+            const int off = carry + incl - v.w + (w ? wsum[w - 1] : 0);
+            if (i < n4) *reinterpret_cast<int4 *>(cell_start + i) = make_int4(v.x + off, v.y + off, v.z + off, v.w + off);
+            carry += wsum[31];
+        }
+        __threadfence();
+        __syncthreads();
+        // ---- scatter from the end of each cell; afterwards cell_start[c] = start of cell c, cell_start[ncell] = n ----
+        for (int k = tid; k < n; k += BQG_BUILD_T) {
+            const float x = xyz[(size_t)k * 3], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
+            const int c = (bqg_cell(z, h.oz, h.inv_c, h.dimz) * h.dimy + bqg_cell(y, h.oy, h.inv_c, h.dimy)) * h.dimx +
+                          bqg_cell(x, h.ox, h.inv_c, h.dimx);
+            const int pos = atomicSub(cell_start + c, 1) - 1;
+            sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+        }
+        return;
+    }
 
     // ---- histogram ----
     for (int i = tid; i < ncell; i += BQG_BUILD_T) cnt[i] = 0;
@@ -297,7 +363,7 @@ bq_grid_query_kernel(int n, int m, float r_abs, float r2_in, float r2_out, int n
     const unsigned char *ws = ws_all + (size_t)bs * ws_stride;
     const BQGridHeader h = *reinterpret_cast<const BQGridHeader *>(ws);
     const int *cell_start = reinterpret_cast<const int *>(ws + sizeof(BQGridHeader));
-    const float4 *sorted = reinterpret_cast<const float4 *>(ws + sizeof(BQGridHeader) + sizeof(int) * (size_t)(BQG_CAP + 4));
+    const float4 *sorted = reinterpret_cast<const float4 *>(ws + bqg_sorted_off(n));
     int *list = lists + (size_t)tid * pitch;
 
     int L = 0;
@@ -401,7 +467,7 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
         }
         static bool configured[4] = {false, false, false, false};
         if (!configured[3]) {
-            cudaError_t e = cudaFuncSetAttribute(bq_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_CAP * 4);
+            cudaError_t e = cudaFuncSetAttribute(bq_grid_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_CAP * 4);
             if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query grid smem attribute");
             configured[3] = true;
         }
@@ -411,7 +477,8 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
             configured[MODE] = true;
         }
         const float r_abs = fabsf(r_out);
-        bq_grid_build_kernel<<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
+        if (n > BQG_BIG_N) bq_grid_build_kernel<true><<<b, BQG_BUILD_T, 0, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
+        else bq_grid_build_kernel<false><<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
         DE6D_CHECK_LAUNCH("bq_grid_build_kernel");
         double lim = 3.0 * sqrt((double)nsample * (double)n);
         if (lim < 1024.0) lim = 1024.0;

@@ -281,6 +281,19 @@ def test_ball_query_radius_boundary_and_degenerate_clouds(orc, impl):
     _bq_check(orc, _bq_all(impl, r, ns, cu(bad), cu(new_xyz)), r, ns, bad, new_xyz)
 
 
+@pytest.mark.parametrize("N,M,r,ns", [(131072, 700, 0.2, 64), (40000, 300, 1.0, 32), (131072, 200, 6.0, 16)])
+def test_ball_query_large_clouds(orc, N, M, r, ns):
+    """BASELINE configs[4] shape (131072-point LiDAR-ring frames, ns = 64): the large-cloud grid (histogram in global
+    memory, up to 2^21 cells) against the oracle and the brute-force kernel; r = 6 m exercises the per-query fallback."""
+    xyz = synth.lidar_clouds(2, N, seed=N)
+    new_xyz = np.ascontiguousarray(xyz[:, :: N // M][:, :M]) + np.float32(0.01)
+    new_xyz[:, -2:] += 1000.0
+    got = _bq_all(2, r, ns, cu(xyz), cu(new_xyz))
+    _bq_check(orc, got, r, ns, xyz, new_xyz)
+    brute = _bq_all(1, r, ns, cu(xyz), cu(new_xyz))
+    np.testing.assert_array_equal(got["cnt"][1], brute["cnt"][1]); np.testing.assert_array_equal(got["plain"], brute["plain"])
+
+
 def test_ball_query_full_size_grid_equals_brute_force(ops):
     """BASELINE layer-1 shape (16 x 16384 points, 4096 queries, r in {0.2, 0.4, 0.8}): the grid kernel and the
     brute-force kernel agree bit for bit on uniform and on LiDAR-ring clouds; rows are ascending up to the count."""
