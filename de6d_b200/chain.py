@@ -133,16 +133,19 @@ class OpChain:
             self.inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
             self.nms = BatchedNMS(self.batch, self.cfg.n_proposals, device=self.device)
 
-    def load(self, host, stream=None):
+    SENSOR_KEYS = ("xyz", "feats0")   # what a deployment copies per frame: points + intensity
+
+    def load(self, host, stream=None, keys=None):
         if self.inputs is None:
             self._alloc_like(host)
         s = stream or self.main
         with torch.cuda.stream(s):
             for k, v in host.items():
-                self.inputs[k].copy_(v, non_blocking=True)
+                if keys is None or k in keys:
+                    self.inputs[k].copy_(v, non_blocking=True)
 
-    def h2d_bytes(self):
-        return sum(v.numel() * v.element_size() for v in self.inputs.values())
+    def h2d_bytes(self, keys=None):
+        return sum(v.numel() * v.element_size() for k, v in self.inputs.items() if keys is None or k in keys)
 
     # ---- the chain --------------------------------------------------------------------------------
     def _group_scales(self, xyz, new_xyz, feats, radii, nsamples, after, outs, tag):
@@ -275,9 +278,11 @@ class OpChain:
     def d2h_bytes(self):
         return sum(v.numel() * v.element_size() for v in self.result_tensors().values())
 
-    def step_host(self, host, sync=True):
-        """Public end-to-end call: pinned host inputs -> device, run, results -> pinned host."""
-        self.load(host)
+    def step_host(self, host, sync=True, keys=None):
+        """Public end-to-end call: pinned host inputs -> device, run, results -> pinned host.  keys: copy only these
+        inputs (e.g. SENSOR_KEYS: in the real detector the per-layer features, S-FPS scores and proposals are products
+        of the MLPs / head on the device; here they are synthetic stand-ins that `load` made resident)."""
+        self.load(host, keys=keys)
         if self.graph is None and self.outputs is None:
             self.capture()
         self.step()

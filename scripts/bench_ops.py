@@ -118,3 +118,8 @@ print("stress ball_query_cnt r=0.2 ns=64 M=16384 : %8.3f ms" % timeit(lambda: pu
 xyz = cu(synth.clouds(B, 4096, seed=1))
 f = cu(synth.features(B, 64, 4096, seed=1)).permute(0, 2, 1)
 print("fused F-FPS B=%d n=4096 c=64 m=512 : %8.3f ms" % (B, timeit(lambda: pu.furthest_point_sample_features(xyz, f, 1.0, 512))))
+# S-FPS at the layer-1 size (not on the SASA chain, where S-FPS samples 512 points): registers hold weights too
+xyz = cu(synth.clouds(B, 16384, seed=0)); wts = cu(synth.weights(B, 16384, seed=1))
+print("S-FPS B=%d 16384->4096 : %8.3f ms" % (B, timeit(lambda: pu.furthest_point_sample_weights(xyz, wts, 4096), reps=5)))
+xyz = cu(synth.clouds(B, 4096, seed=0)); wts = cu(synth.weights(B, 4096, seed=1))
+print("S-FPS B=%d 4096->512 : %8.3f ms" % (B, timeit(lambda: pu.furthest_point_sample_weights(xyz, wts, 512), reps=5)))

@@ -13,4 +13,4 @@ echo "== smoke" ; timeout 600 python __graft_entry__.py smoke > $OUT/smoke_$TAG.
 echo "== bench" ; timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err ; echo "bench rc=$?" ; tail -3 $OUT/bench_$TAG.err ; head -c 400 $OUT/bench_$TAG.json; echo
 echo "== bench reference arm" ; timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err ; echo "rc=$?"; head -c 300 $OUT/bench_ref_$TAG.json; echo
 echo "== ncu launches" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_$TAG.csv python scripts/ncu_chain.py > $OUT/ncu_launches_$TAG.log 2>&1 ; echo "ncu rc=$?"
-echo "== ncu full, one step" ; DE6D_STEPS=0 DE6D_TRACE=$OUT/prof_step_$TAG.trace.json timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:fps_|group_|bq_grid|nms_kernel|ball_query_kernel|dist_matrix|iou_matrix" -c 80 -f -o $OUT/prof_step_$TAG python scripts/ncu_chain.py > $OUT/prof_step_$TAG.log 2>&1 ; echo "ncu rc=$?"; ls -la $OUT/prof_step_$TAG.ncu-rep
+echo "== ncu full, one step" ; DE6D_STEPS=0 DE6D_TRACE=$OUT/prof_step_$TAG.trace.json timeout 1500 ncu --set full --clock-control none -k "regex:fps_|group_|bq_grid|nms_kernel|ball_query_kernel|dist_matrix|iou_matrix" -c 80 -f -o /tmp/prof_step_$TAG python scripts/ncu_chain.py > $OUT/prof_step_$TAG.log 2>&1 ; echo "ncu rc=$?"; ncu -i /tmp/prof_step_$TAG.ncu-rep --page raw --csv > $OUT/prof_step_${TAG}_raw.csv 2>/dev/null; ls -la $OUT/prof_step_${TAG}_raw.csv

@@ -1,51 +1,64 @@
 #!/usr/bin/env python
-"""Builds profiles/ncu_traffic.json: DRAM bytes per launch of the kernels behind the bench's C-ABI entry points, read
-from `ncu --set full` reports of scripts/ncu_chain.py (same workload as bench.py, batch 64, eager, one stream).
-    python scripts/ncu_traffic.py gpurun_out/prof_A.ncu-rep [more.ncu-rep ...]
-The mapping kernel -> (entry point, shape) is positional: ncu_chain.py prints the entry-point sequence of one step
-(DE6D_TRACE=1) into <rep>.trace.json, and the k-th captured launch of a kernel name is matched to the k-th call whose
-entry point launches that kernel."""
+"""Builds profiles/ncu_traffic.json: DRAM bytes per C-ABI call (summed over the kernels the call launches) for the
+bench workload, from an `ncu --set full` capture of scripts/ncu_chain.py (same chain as bench.py, batch 64, eager,
+one stream) exported with `ncu -i X.ncu-rep --page raw --csv`.
+    python scripts/ncu_traffic.py gpurun_out/prof_step_TAG_raw.csv
+The capture is walked in lockstep with the entry-point sequence of one step (X.trace.json, written by ncu_chain.py
+with DE6D_TRACE): each entry point expands to the kernels it launches."""
 import csv
-import io
 import json
 import os
-import subprocess
 import sys
 
-KERNEL_OF = {   # kernel-name substring -> entry point
-    "fps_bucket_kernel<0": "de6d_furthest_point_sampling", "fps_bucket_kernel<1": "de6d_furthest_point_sampling_weights",
-    "fps_features_kernel": "de6d_furthest_point_sampling_features", "group_staged_kernel": "de6d_group_concat",
-    "group_direct_kernel": "de6d_group_concat",
-    "bq_grid_query_kernel": "de6d_ball_query_ex", "nms_kernel": "de6d_nms_batched", "dist_matrix_kernel": "de6d_dist_matrix",
-    "fps_matrix_kernel": "de6d_furthest_point_sampling_matrix",
-}
 out_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
-table = json.load(open(out_path)) if os.path.exists(out_path) else {}
+
+
+def kernels_of(entry, shape):
+    if entry in ("de6d_furthest_point_sampling", "de6d_furthest_point_sampling_weights"):
+        return ["fps_"]
+    if entry == "de6d_furthest_point_sampling_features":
+        return ["fps_features_kernel"]
+    if entry == "de6d_furthest_point_sampling_matrix":
+        return ["fps_matrix_kernel"]
+    if entry == "de6d_dist_matrix":
+        return ["dist_matrix_kernel"]
+    if entry in ("de6d_gather_points", "de6d_group_points"):
+        return ["group_"]
+    if entry == "de6d_group_concat":
+        return ["group_xyz_center_kernel", "group_"] if shape[1] > 0 else ["group_xyz_center_kernel"]
+    if entry == "de6d_ball_query_ex":
+        return ["bq_grid_build_kernel", "bq_grid_query_kernel"] if shape[3] >= 2048 else ["ball_query_kernel"]
+    if entry == "de6d_nms_batched":
+        return ["nms_kernel"]
+    return []
+
+
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3}
+table = {}
 for rep in sys.argv[1:]:
-    trace = json.load(open(rep.replace(".ncu-rep", ".trace.json")))   # [[entry, [shape...]], ...] of ONE step
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr = rows[0]
-    seen = {}
-    for r in rows[2:]:
-        d = dict(zip(hdr, r))
-        name = d["Kernel Name"]
-        entry = next((e for k, e in KERNEL_OF.items() if k in name), None)
-        if entry is None:
-            continue
-        calls = [t for t in trace if t[0] == entry]
-        i = seen.get(entry, 0)
-        seen[entry] = i + 1
-        if not calls:
-            continue
-        shape = calls[i % len(calls)][1]
-        def val(key):
-            v, u = float(d[key].replace(",", "")), rows[1][hdr.index(key)]
-            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    trace = json.load(open(rep.replace("_raw.csv", ".trace.json")))
+    rows = list(csv.reader(open(rep)))
+    hdr, units = rows[0], rows[1]
+    launches = [dict(zip(hdr, r)) for r in rows[2:]]
+
+    def val(d, key):
+        return float(d[key].replace(",", "")) * UNIT[units[hdr.index(key)]]
+
+    pos = 0
+    for entry, shape in trace:
+        names = kernels_of(entry, shape)
+        rec = {"kernels": [], "dram_bytes": 0, "dram_read": 0, "dram_write": 0, "ncu_duration_us": 0.0, "report": os.path.basename(rep)}
+        for want in names:
+            assert pos < len(launches) and want in launches[pos]["Kernel Name"], (entry, shape, want, launches[pos]["Kernel Name"] if pos < len(launches) else None)
+            d = launches[pos]
+            pos += 1
+            rec["kernels"].append(d["Kernel Name"].split("(")[0].replace("void ", ""))
+            rec["dram_read"] += int(val(d, "dram__bytes_read.sum"))
+            rec["dram_write"] += int(val(d, "dram__bytes_write.sum"))
+            rec["ncu_duration_us"] += val(d, "gpu__time_duration.sum")
+        rec["dram_bytes"] = rec["dram_read"] + rec["dram_write"]
         key = entry + ":" + ",".join(str(x) for x in shape)
-        table[key] = {"kernel": name.split("(")[0], "dram_bytes": int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum")),
-                      "dram_read": int(val("dram__bytes_read.sum")), "dram_write": int(val("dram__bytes_write.sum")),
-                      "ncu_duration_us": float(d["gpu__time_duration.sum"].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}[rows[1][hdr.index("gpu__time_duration.sum")]],
-                      "report": os.path.basename(rep)}
+        if key not in table:          # first occurrence of a shape (the three radius scales share sizes but not radii)
+            table[key] = rec
 json.dump(table, open(out_path, "w"), indent=1, sort_keys=True)
 print("wrote", out_path, len(table), "entries")
