@@ -261,10 +261,14 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from de6d_b200 import build as de6d_build
-    de6d_build.build()
-    from de6d_b200 import _lib, chain as ch, dist as ddist
+    from de6d_b200 import dist as ddist
 
     rank, world, local = ddist.init_from_env()
+    if rank == 0:
+        de6d_build.build()           # no-op when lib/libde6d_b200.so is newer than csrc/ (it travels with the repo)
+    if world > 1:
+        dist.barrier()               # the other ranks only load the library
+    from de6d_b200 import _lib, chain as ch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the op chain has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)

@@ -52,7 +52,9 @@ def build(force=False, verbose=False):
         outs = list(ex.map(run, cmds))
     if verbose:
         print("\n".join(outs))
-    run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    tmp = LIB + ".%d.tmp" % os.getpid()     # link next to the target, then rename: concurrent loaders never see a partial file
+    run([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    os.replace(tmp, LIB)
     return LIB
 
 
