@@ -234,7 +234,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    args.emit(json.dumps(line))
     return 0
 
 
@@ -437,10 +437,24 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu,
             "detections_all_gather_ms": gather_ms,
         }
-        print(json.dumps(line), flush=True)
+        args.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Route everything that libraries print on fd 1 (e.g. NCCL's version banner) to stderr; returns a writer for
+    the one JSON line that must be the only thing on stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(saved, "w")
+
+    def emit(line):
+        out.write(line + "\n")
+        out.flush()
+    return emit
 
 
 def main():
@@ -454,6 +468,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
+    args.emit = _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)
