@@ -45,6 +45,7 @@ PROTOTYPES = {
     "de6d_nms_workspace_init": [_i, _p, _p],
     "de6d_nms_batched": [_i, _i, _p, _p, _f, _i, _p, _p, _p, _sz, _p],
     "de6d_points_in_boxes": [_i, _i, _i, _p, _p, _p, _p],
+    "de6d_points_in_boxes9": [_i, _i, _i, _p, _p, _p, _p],
     "de6d_points_in_boxes_mask": [_i, _i, _p, _p, _p, _p],
     "de6d_last_error_string": [],
     "de6d_version": [],

@@ -106,9 +106,84 @@ points_in_boxes_mask_kernel(int t, int m, const float *__restrict__ boxes, const
     for (int i = 0; i < tn; ++i) out[(size_t)(k0 + i) * m + j] = inside<true>(sb[i], x, y, z) ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Full-pose (9-DoF) boxes [x, y, z, dx, dy, dz, rz, ry, rx]: Det6D's own target assignment
+// (point_head_box6d_vote.py:198-209,284-286) calls box_utils.points_in_boxes3d (box_utils.py:110-124), which builds
+// the 8 corners with scipy Rotation.from_euler('zyx', (rz, ry, rx)) in float64 and tests every point against a
+// Delaunay triangulation of each box on the HOST, one box at a time; a later box overwrites an earlier one.
+// Here: R = Rx(rx) Ry(ry) Rz(rz) (the same extrinsic z-y-x composition) once per box in double, the point is
+// inside iff |R^T (p - c)| <= d / 2 on all three axes (the convex hull of the corners is exactly that box), and
+// the LAST containing box wins.  Double arithmetic like the reference, so only points within ~1e-15 of a face can
+// be classified differently.
+// ---------------------------------------------------------------------------------------------------------
+struct Box9Pre {
+    double r[9];       // rotation matrix, row-major: world = R * local
+    double c[3], h[3]; // centre, half extents
+};
+
+__global__ void __launch_bounds__(PIB_THREADS)
+points_in_boxes9_kernel(int t, int m, const float *__restrict__ boxes, const float *__restrict__ pts,
+                        long long *__restrict__ out) {
+    constexpr int TILE = 64;
+    __shared__ Box9Pre sb[TILE];
+    const int bs = blockIdx.y;
+    const int j = blockIdx.x * PIB_THREADS + threadIdx.x;
+    boxes += (size_t)bs * t * 9;
+    const bool ok = j < m;
+    double x = 0, y = 0, z = 0;
+    if (ok) {
+        const float *p = pts + ((size_t)bs * m + j) * 3;
+        x = p[0]; y = p[1]; z = p[2];
+    }
+    long long found = -1;
+    for (int base = 0; base < t; base += TILE) {
+        const int tn = min(TILE, t - base);
+        __syncthreads();
+        if (threadIdx.x < tn) {
+            const float *b = boxes + (size_t)(base + threadIdx.x) * 9;
+            Box9Pre q;
+            const double rz = b[6], ry = b[7], rx = b[8];
+            const double cz = cos(rz), sz = sin(rz), cy = cos(ry), sy = sin(ry), cx = cos(rx), sx = sin(rx);
+            // Rx(rx) * Ry(ry) * Rz(rz)
+            q.r[0] = cy * cz;                 q.r[1] = -cy * sz;                q.r[2] = sy;
+            q.r[3] = sx * sy * cz + cx * sz;  q.r[4] = -sx * sy * sz + cx * cz; q.r[5] = -sx * cy;
+            q.r[6] = -cx * sy * cz + sx * sz; q.r[7] = cx * sy * sz + sx * cz;  q.r[8] = cx * cy;
+            q.c[0] = b[0]; q.c[1] = b[1]; q.c[2] = b[2];
+            q.h[0] = (double)b[3] / 2.0; q.h[1] = (double)b[4] / 2.0; q.h[2] = (double)b[5] / 2.0;
+            sb[threadIdx.x] = q;
+        }
+        __syncthreads();
+        if (ok) {
+            for (int i = 0; i < tn; ++i) {
+                const Box9Pre &q = sb[i];
+                const double dx = x - q.c[0], dy = y - q.c[1], dz = z - q.c[2];
+                const double lx = q.r[0] * dx + q.r[3] * dy + q.r[6] * dz;   // R^T (p - c)
+                const double ly = q.r[1] * dx + q.r[4] * dy + q.r[7] * dz;
+                const double lz = q.r[2] * dx + q.r[5] * dy + q.r[8] * dz;
+                if (fabs(lx) <= q.h[0] && fabs(ly) <= q.h[1] && fabs(lz) <= q.h[2]) found = base + i;
+            }
+        }
+    }
+    if (ok) out[(size_t)bs * m + j] = found;
+}
+
 }  // namespace de6d
 
 using namespace de6d;
+
+// box_utils.points_in_boxes3d (pcdet/utils/box_utils.py:110-124), batched and on the device: boxes (b,t,9)
+// [x,y,z,dx,dy,dz,rz,ry,rx], pts (b,m,3) -> out (b,m) int64 = index of the LAST box containing the point, -1 if none.
+extern "C" int de6d_points_in_boxes9(int b, int t, int m, const float *boxes, const float *pts, long long *out,
+                                     cudaStream_t stream) {
+    if (b < 0 || t < 0 || m < 0) return de6d_set_error(DE6D_ERR_INVALID, "points_in_boxes9: negative size");
+    if (b == 0 || m == 0) return DE6D_OK;
+    if (!pts || !out || (t > 0 && !boxes)) return de6d_set_error(DE6D_ERR_INVALID, "points_in_boxes9: null pointer");
+    if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "points_in_boxes9: batch > 65535");
+    dim3 grid(ceil_div(m, PIB_THREADS), b);
+    points_in_boxes9_kernel<<<grid, PIB_THREADS, 0, stream>>>(t, m, boxes, pts, out);
+    DE6D_CHECK_LAUNCH("points_in_boxes9_kernel");
+    return DE6D_OK;
+}
 
 extern "C" int de6d_points_in_boxes(int b, int t, int m, const float *boxes, const float *pts, int *box_idx_of_points,
                                     cudaStream_t stream) {

@@ -183,6 +183,14 @@ int de6d_points_in_boxes(int b, int t, int m, const float *boxes, const float *p
 int de6d_points_in_boxes_mask(int t, int m, const float *boxes, const float *pts, int *point_indices,
                               cudaStream_t stream);
 
+/* ---- next to the path: full-pose boxes -------------------------------------------------- */
+
+/* box_utils.points_in_boxes3d(points, boxes3d)   pcdet/utils/box_utils.py:110-124 (host numpy + scipy Delaunay per box in
+ * the reference; called by the Det6D head's target assignment, point_head_box6d_vote.py:198-209,284-286), batched:
+ * boxes (b,t,9) [x,y,z,dx,dy,dz,rz,ry,rx] (scipy 'zyx' Euler convention), pts (b,m,3) -> out (b,m) int64 = index of the
+ * LAST box containing the point (later boxes overwrite earlier ones, like the reference loop), -1 if none. */
+int de6d_points_in_boxes9(int b, int t, int m, const float *boxes, const float *pts, long long *out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

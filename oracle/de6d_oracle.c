@@ -533,3 +533,29 @@ ORC_API void orc_points_in_boxes_cpu(int t, int m, const float *boxes, const flo
     for (int k = 0; k < t; ++k)
         for (int j = 0; j < m; ++j) out[(size_t)k * m + j] = pt_in_box_host(pts + (size_t)j * 3, boxes + (size_t)k * 7);
 }
+
+/* box_utils.points_in_boxes3d: pcdet/utils/box_utils.py:59-72 (corners from scipy Rotation.from_euler('zyx', (rz, ry, rx)),
+ * float64) + :110-124 (Delaunay in_hull per box, later boxes overwrite).  Third-party pieces: scipy 1.x Rotation
+ * (extrinsic z, then y, then x: R = Rx Ry Rz) and Delaunay.find_simplex >= 0, i.e. membership in the convex hull of the
+ * 8 corners -- the box itself -- so the test is restated as |R^T (p - c)| <= d / 2 in double.  tests/test_oracle.py
+ * pins this against scipy's own Rotation + Delaunay on random points away from faces.
+ * boxes (t, 9) [x,y,z,dx,dy,dz,rz,ry,rx], pts (m, 3) -> flags (m) int64. */
+ORC_API void orc_points_in_boxes9(int t, int m, const float *boxes, const float *pts, long long *flags) {
+    for (int j = 0; j < m; ++j) flags[j] = -1;
+    for (int i = 0; i < t; ++i) {
+        const float *b = boxes + (size_t)i * 9;
+        const double rz = b[6], ry = b[7], rx = b[8];
+        const double cz = cos(rz), sz = sin(rz), cy = cos(ry), sy = sin(ry), cx = cos(rx), sx = sin(rx);
+        const double r[9] = {cy * cz, -cy * sz, sy,
+                             sx * sy * cz + cx * sz, -sx * sy * sz + cx * cz, -sx * cy,
+                             -cx * sy * cz + sx * sz, cx * sy * sz + sx * cz, cx * cy};
+        const double hx = (double)b[3] / 2.0, hy = (double)b[4] / 2.0, hz = (double)b[5] / 2.0;
+        for (int j = 0; j < m; ++j) {
+            const double dx = (double)pts[j * 3] - b[0], dy = (double)pts[j * 3 + 1] - b[1], dz = (double)pts[j * 3 + 2] - b[2];
+            const double lx = r[0] * dx + r[3] * dy + r[6] * dz;
+            const double ly = r[1] * dx + r[4] * dy + r[7] * dz;
+            const double lz = r[2] * dx + r[5] * dy + r[8] * dz;
+            if (fabs(lx) <= hx && fabs(ly) <= hy && fabs(lz) <= hz) flags[j] = i;
+        }
+    }
+}

@@ -243,3 +243,12 @@ def points_in_boxes_cpu(points, boxes):
     out = np.zeros((boxes.shape[0], points.shape[0]), np.int32)
     lib().orc_points_in_boxes_cpu(boxes.shape[0], points.shape[0], _fp(boxes), _fp(points), _ip(out))
     return out
+
+
+def points_in_boxes3d(points, boxes3d):
+    """box_utils.points_in_boxes3d (pcdet/utils/box_utils.py:110-124): points (n, 3+), boxes (m, 9) -> (n,) int64."""
+    pts = _f32(np.asarray(points)[:, :3]); boxes = _f32(boxes3d)
+    assert boxes.shape[-1] == 9
+    out = np.full(pts.shape[0], -1, np.int64)
+    lib().orc_points_in_boxes9(boxes.shape[0], pts.shape[0], _fp(boxes), _fp(pts), out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out

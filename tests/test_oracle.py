@@ -173,3 +173,28 @@ def test_dist_matrix_against_float64(orc):
     np.testing.assert_allclose(got, ref, rtol=2e-6, atol=1e-6)
     np.testing.assert_array_equal(got, got.transpose(0, 2, 1))
     assert (np.diagonal(got, axis1=1, axis2=2) == 0).all()
+
+
+def test_points_in_boxes3d_against_scipy(orc):
+    """orc.points_in_boxes3d against scipy's own Rotation.from_euler('zyx') + Delaunay.find_simplex, the two
+    third-party pieces box_utils.points_in_boxes3d (box_utils.py:59-72,110-124) is made of; points closer than 1e-6 m
+    to a box face are excluded (Delaunay's own tolerance decides those)."""
+    from scipy.spatial import Delaunay
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(3)
+    T, M = 14, 4000
+    boxes = np.concatenate([synth.boxes(1, T, seed=8)[0][:, :7], rng.uniform(-0.4, 0.4, (T, 2)).astype(np.float32)], 1)
+    boxes[5, :3] = boxes[4, :3] + 0.3                                  # overlapping boxes: the later one must win
+    pts = (boxes[rng.integers(0, T, M), :3] + rng.normal(0, 1.2, (M, 3))).astype(np.float32)
+    got = orc.points_in_boxes3d(pts, boxes)
+    template = np.array([[1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, -1], [1, 1, 1], [1, -1, 1], [-1, -1, 1], [-1, 1, 1]]) / 2
+    want = np.full(M, -1, np.int64)
+    near = np.zeros(M, bool)
+    for i in range(T):
+        R = Rotation.from_euler("zyx", boxes[i, 6:9].astype(np.float64)).as_matrix()
+        corners = (boxes[i, 3:6].astype(np.float64) * template) @ R.T + boxes[i, :3].astype(np.float64)
+        want[Delaunay(corners).find_simplex(pts.astype(np.float64)) >= 0] = i
+        local = (pts.astype(np.float64) - boxes[i, :3]) @ R
+        near |= (np.abs(np.abs(local) - boxes[i, 3:6] / 2.0) < 1e-6).any(1)
+    assert (want >= 0).sum() > 500 and (want == 5).sum() > 10
+    np.testing.assert_array_equal(got[~near], want[~near])

@@ -486,6 +486,38 @@ def test_nms_batched_matches_per_frame(orc, ops):
     assert torch.equal(n1, n2) and torch.equal(k1, k2)
 
 
+def test_class_agnostic_nms_batched_equals_reference_loop(orc, ops):
+    """model_nms_utils: the batched, sync-free post-processing selects per frame exactly what the reference's Python
+    loop (score mask -> topk -> nms_gpu -> index mapping, model_nms_utils.py:6-25) selects, and that loop run on this
+    package's nms_gpu equals the same loop evaluated with the oracle."""
+    from de6d_b200 import model_nms_utils as mu
+    F, n = 6, 512
+    bx, sc = synth.proposals(F, n, seed=21)
+    bx9 = np.concatenate([bx, np.zeros((F, n, 2), np.float32)], -1)          # (x, y, z, dx, dy, dz, rz, ry, rx): extra columns ignored
+    cfg = {"NMS_TYPE": "nms_gpu", "NMS_THRESH": 0.1, "NMS_PRE_MAXSIZE": 300, "NMS_POST_MAXSIZE": 40}
+    thr = 0.35
+    sel, ssc, num = mu.class_agnostic_nms_batched(cu(sc), cu(bx9), cfg, score_thresh=thr)
+    sel, ssc, num = sel.cpu().numpy(), ssc.cpu().numpy(), num.cpu().numpy()
+    for f in range(F):
+        s1, sc1 = mu.class_agnostic_nms(cu(sc[f]), cu(bx9[f]), cfg, score_thresh=thr)
+        s1 = s1.cpu().numpy()
+        # oracle version of the same loop
+        idx = np.nonzero(sc[f] >= thr)[0]
+        top = idx[np.argsort(-sc[f][idx], kind="stable")][:300]
+        keep = orc.nms_sorted(np.ascontiguousarray(bx[f][top]), 0.1)[:40]
+        np.testing.assert_array_equal(s1, top[keep])
+        assert num[f] == len(s1)
+        np.testing.assert_array_equal(sel[f, :num[f]], s1)
+        assert (sel[f, num[f]:] == -1).all()
+        np.testing.assert_array_equal(ssc[f, :num[f]], sc[f][s1])
+    # no threshold, frame with nothing above threshold
+    sel2, _, num2 = mu.class_agnostic_nms_batched(cu(sc), cu(bx9), cfg, score_thresh=2.0)
+    assert int(num2.sum()) == 0 and bool((sel2 == -1).all())
+    sel3, _, num3 = mu.class_agnostic_nms_batched(cu(sc), cu(bx9), cfg, score_thresh=None)
+    s3, _ = mu.class_agnostic_nms(cu(sc[0]), cu(bx9[0]), cfg, score_thresh=None)
+    np.testing.assert_array_equal(sel3[0, :int(num3[0])].cpu().numpy(), s3.cpu().numpy())
+
+
 def test_points_in_boxes_vs_oracle(orc, ops):
     ru = ops[2]
     B, T, M = 3, 100, 16384
@@ -503,6 +535,28 @@ def test_points_in_boxes_vs_oracle(orc, ops):
     assert len(bad) == 0, "%d mismatches, first %s" % (len(bad), bad[:5])
     mask = ru.points_in_boxes_cpu(pts[0], boxes[0])       # numpy in/out, device compute, MARGIN 1e-2 mask
     np.testing.assert_array_equal(mask, orc.points_in_boxes_cpu(pts[0], boxes[0]))
+
+
+def test_points_in_boxes3d_full_pose_vs_oracle(orc):
+    """box_utils.points_in_boxes3d (9-DoF boxes, Det6D target assignment) on the device vs the oracle."""
+    from de6d_b200 import box_utils
+    rng = np.random.default_rng(5)
+    B, T, M = 3, 70, 16384
+    boxes = np.concatenate([synth.boxes(B, T, seed=9)[..., :7], rng.uniform(-0.5, 0.5, (B, T, 2)).astype(np.float32)], -1)
+    boxes[:, 11, :3] = boxes[:, 10, :3] + 0.2
+    pts = synth.clouds(B, M, seed=4)
+    for b in range(B):
+        pts[b, :7000] = (boxes[b, rng.integers(0, T, 7000), :3] + rng.normal(0, 1.0, (7000, 3))).astype(np.float32)
+    got = box_utils.points_in_boxes3d_batched(cu(pts), cu(boxes)).cpu().numpy()
+    for b in range(B):
+        want = orc.points_in_boxes3d(pts[b], boxes[b])
+        assert (want >= 0).sum() > 2000
+        np.testing.assert_array_equal(got[b], want)
+    one = box_utils.points_in_boxes3d(pts[0], boxes[0])                 # numpy in / numpy out, reference signature
+    assert isinstance(one, np.ndarray) and one.dtype == np.int64
+    np.testing.assert_array_equal(one, got[0])
+    t = box_utils.points_in_boxes3d(cu(pts[1]), cu(boxes[1]))
+    assert t.is_cuda and torch.equal(t.cpu(), torch.from_numpy(got[1]))
 
 
 # ------------------------------------------------------------------------------------------------ golden vectors (reference CUDA kernels)
