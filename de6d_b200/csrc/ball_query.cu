@@ -465,17 +465,9 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
         } else if (workspace_bytes < need) {
             return de6d_set_error(DE6D_ERR_INVALID, "ball_query: workspace too small");
         }
-        static bool configured[4] = {false, false, false, false};
-        if (!configured[3]) {
-            cudaError_t e = cudaFuncSetAttribute(bq_grid_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_CAP * 4);
-            if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query grid smem attribute");
-            configured[3] = true;
-        }
-        if (!configured[MODE]) {
-            cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query query smem attribute");
-            configured[MODE] = true;
-        }
+        static unsigned long long dev_build = 0, dev_query = 0;   // per call site (one per MODE instantiation)
+        if (int rc = de6d_ensure_smem(bq_grid_build_kernel<false>, BQG_CAP * 4, dev_build, "ball_query grid smem attribute")) return rc;
+        if (int rc = de6d_ensure_smem(bq_grid_query_kernel<MODE>, 160 * 1024, dev_query, "ball_query query smem attribute")) return rc;
         const float r_abs = fabsf(r_out);
         if (n > BQG_BIG_N) bq_grid_build_kernel<true><<<b, BQG_BUILD_T, 0, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
         else bq_grid_build_kernel<false><<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
@@ -496,12 +488,9 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
 
     size_t smem = (size_t)BQ_TILE * 12 + (size_t)BQ_QPB * (nsample > 0 ? nsample : 1) * sizeof(int);
     if (smem > 200 * 1024) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: nsample too large");
-    static size_t configured_bf = 0;
-    if (smem > 48 * 1024 && smem > configured_bf) {
-        cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query smem attribute");
-        configured_bf = 200 * 1024;
-    }
+    static unsigned long long dev_bf = 0;
+    if (smem > 48 * 1024)
+        if (int rc = de6d_ensure_smem(ball_query_kernel<MODE>, 200 * 1024, dev_bf, "ball_query smem attribute")) return rc;
     dim3 grid(ceil_div(m, BQ_QPB), b);
     ball_query_kernel<MODE><<<grid, BQ_NWARP * 32, smem, s>>>(n, m, r2_in, r2_out, nsample, new_xyz, xyz, idx_cnt, idx);
     DE6D_CHECK_LAUNCH("ball_query_kernel");

@@ -67,3 +67,16 @@ void de6d_count_launch(void);
         if (e__ != cudaSuccess) return de6d_set_cuda_error(e__, where); \
         de6d_count_launch();                                      \
     } while (0)
+
+// Dynamic shared memory above 48 KB is an opt-in attribute of a (function, device) pair: set it once per pair.
+// `mask` is a per-call-site static bit set of the devices already configured (race-benign: setting twice is harmless).
+template <typename F>
+static inline int de6d_ensure_smem(F func, int bytes, unsigned long long &mask, const char *what) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return DE6D_OK;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return de6d_set_cuda_error(e, what);
+    if (dev >= 0 && dev < 64) mask |= 1ull << dev;
+    return DE6D_OK;
+}

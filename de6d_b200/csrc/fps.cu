@@ -615,13 +615,8 @@ static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float 
                          int *idx, cudaStream_t s) {
     constexpr int CAP = NW * BPW * 32;
     size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16;
-    static bool configured = false;  // attribute is per-function, set once per process (idempotent, race-benign)
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel<MODE, NW, BPW, PRUNE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return de6d_set_cuda_error(e, "fps smem attribute");
-        configured = true;
-    }
+    static unsigned long long devs = 0;
+    if (int rc = de6d_ensure_smem(fps_bucket_kernel<MODE, NW, BPW, PRUNE>, (int)smem, devs, "fps smem attribute")) return rc;
     fps_bucket_kernel<MODE, NW, BPW, PRUNE><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
     DE6D_CHECK_LAUNCH("fps_bucket_kernel");
     return DE6D_OK;
@@ -633,12 +628,8 @@ static int launch_bucket_cluster(int b, int n, int m, const float *xyz, float *t
     const int S = (n + CAP - 1) / CAP;
     size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16;
     auto kern = fps_bucket_kernel<FPS_D, NW, BPW, true, true>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return de6d_set_cuda_error(e, "fps cluster smem attribute");
-        configured = true;
-    }
+    static unsigned long long devs = 0;
+    if (int rc = de6d_ensure_smem(kern, (int)smem, devs, "fps cluster smem attribute")) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(S * b));
     cfg.blockDim = dim3(NW * 32);

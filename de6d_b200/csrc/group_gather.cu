@@ -225,13 +225,11 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
         chunk = (chunk + 3) & ~3ll;
         chunks = ceil_div_ll(ms, chunk);
         size_t smem = 128 + (size_t)G * n_pad * 4;
-        static size_t configured[2] = {0, 0};
-        const int t = tma_ok ? 1 : 0;
-        if (smem > 48 * 1024 && configured[t] == 0) {
-            cudaError_t e = tma_ok ? cudaFuncSetAttribute(group_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)
-                                   : cudaFuncSetAttribute(group_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-            if (e != cudaSuccess) return de6d_set_cuda_error(e, "group smem attribute");
-            configured[t] = 1;
+        static unsigned long long devs[2] = {0, 0};
+        if (smem > 48 * 1024) {
+            int rc = tma_ok ? de6d_ensure_smem(group_staged_kernel<true>, 208 * 1024, devs[1], "group smem attribute")
+                            : de6d_ensure_smem(group_staged_kernel<false>, 208 * 1024, devs[0], "group smem attribute");
+            if (rc) return rc;
         }
         dim3 grid((unsigned)chunks, cgroups, b);
         if (tma_ok) group_staged_kernel<true><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride);

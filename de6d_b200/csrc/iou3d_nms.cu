@@ -392,12 +392,11 @@ extern "C" int de6d_nms_batched(int frames, int n, const float *boxes, const int
     int in_smem = smem_full <= 160 * 1024;
     size_t smem = in_smem ? smem_full : (size_t)cb * 8;
     if (smem > 200 * 1024) return de6d_set_error(DE6D_ERR_INVALID, "nms: too many boxes for the sweep");
-    static bool configured[2] = {false, false};
-    if (!configured[normal ? 1 : 0]) {
-        cudaError_t e = normal ? cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-                               : cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return de6d_set_cuda_error(e, "nms smem attribute");
-        configured[normal ? 1 : 0] = true;
+    static unsigned long long devs[2] = {0, 0};
+    {
+        int rc = normal ? de6d_ensure_smem(nms_kernel<true>, 200 * 1024, devs[1], "nms smem attribute")
+                        : de6d_ensure_smem(nms_kernel<false>, 200 * 1024, devs[0], "nms smem attribute");
+        if (rc) return rc;
     }
     dim3 grid((unsigned)tiles, frames);
     if (normal) nms_kernel<true><<<grid, NMS_T, smem, stream>>>(n, boxes, nvalid, thresh, mask, tickets, keep, num_keep, in_smem);
