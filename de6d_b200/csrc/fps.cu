@@ -113,7 +113,18 @@ __device__ __forceinline__ float bucket_lower_bound(float lox, float hix, float 
 // CTA runs the same bucket machinery on its slice; per sample the CTAs exchange one 5-word candidate row (value,
 // global priority, x, y, z) with remote stores that complete on a transaction mbarrier of the destination CTA, and
 // every CTA picks the winner locally -- the selected point's coordinates arrive with the row.
-template <int MODE, int NW, int BPW, bool PRUNE, bool CL = false>
+//
+// SPECK > 1 (D-FPS, single CTA): up to SPECK samples per barrier round, still the exact reference sequence.  Let
+// c1 > c2 > ... be the points ranked by (min-distance desc, tie priority asc) at the start of a round.  c1 is the next
+// sample.  Adding c1 can only lower min-distances, so if c2's own min-distance is untouched by c1 (d(c1,c2) >= temp[c2]
+// with the kernel's rounded distance, temp[c2] > 0) then c2 is still the maximum afterwards, i.e. it IS the sample
+// after c1; likewise c3 if untouched by c1 and c2, and so on.  The round therefore takes the top-SPECK candidates,
+// accepts the longest prefix that passes those pairwise tests, and applies all accepted updates in ONE pass over
+// the (pruned) buckets with ONE barrier.  Candidates come from the per-bucket cached maxima; a point hidden behind
+// its bucket's maximum or behind a warp's two reported maxima could out-rank a candidate, so every bucket also
+// caches its second-best value and every warp reports the largest value it did not report: a candidate is only
+// accepted if it is strictly above that bound.  On FPS workloads ~3.5 of 4 candidates are accepted per round.
+template <int MODE, int NW, int BPW, bool PRUNE, bool CL = false, int SPECK = 1>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict__ xyz_all,
                   const float *__restrict__ w_all, float *__restrict__ temp_all, int *__restrict__ idx_all) {
@@ -121,6 +132,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     constexpr int CAP = NW * BPW * 32;
     static_assert(BPW <= 32, "one owner lane per bucket");
     static_assert(!CL || MODE == FPS_D, "the cluster variant covers D-FPS");
+    static_assert(SPECK == 1 || (MODE == FPS_D && !CL && PRUNE && 2 * NW <= 32), "multi-sample rounds: single-CTA pruned D-FPS");
     if (m <= 0) return;
     int rank = 0, S = 1, cloud = blockIdx.x;
     if (CL) {
@@ -141,6 +153,9 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     int *misc = reinterpret_cast<int *>(red + 6 * NW);            // [0]=pos of index 0, [1]=non-finite flag
     uint32_t *rows = reinterpret_cast<uint32_t *>(misc + 4);      // CL: [2][8][8] candidate rows of the cluster
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(rows + 2 * 8 * 8);   // CL: [2]
+    uint4 *wq = reinterpret_cast<uint4 *>(mbar + 2);              // SPECK: [2][NW] two best bucket maxima of every warp
+    uint32_t *bq = reinterpret_cast<uint32_t *>(wq + 2 * NW);     // SPECK: [2][NW] largest value a warp did not report
+    unsigned short *scp = reinterpret_cast<unsigned short *>(bq + 2 * NW);   // SPECK: [CAP] tie priorities (frees 16 registers)
     unsigned long long *sortbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // aliases sx/sy
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -246,6 +261,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     float blox = INFINITY, bhix = -INFINITY, bloy = INFINITY, bhiy = -INFINITY, bloz = INFINITY, bhiz = -INFINITY;
     float bmaxt = -INFINITY;      // largest min-distance inside the bucket (pruning bound)
     uint32_t bval = 0, bword = 0xffffffffu;  // cached arg-max of the bucket: ord(key) and (cprio<<14 | pos)
+    uint32_t bval2 = 0;                      // SPECK: second-best value of the bucket (hidden behind bval)
 
 #pragma unroll
     for (int j = 0; j < BPW; ++j) {
@@ -264,7 +280,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         }
         sx[p] = x; sy[p] = y; sz[p] = z;
         temp[j] = t0;
-        cpk[j >> 1] |= cp << (16 * (j & 1));
+        if (SPECK > 1) scp[p] = (unsigned short)cp;
+        else cpk[j >> 1] |= cp << (16 * (j & 1));
         if (PRUNE) {
             const bool valid = k != 0xffffffffu;
             uint32_t a0 = __reduce_min_sync(0xffffffffu, valid ? f2ord(x) : 0xffffffffu);
@@ -333,9 +350,15 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         float t = temp[j];
         float val = MODE == FPS_S ? sfps_key(t, wt[j]) : t;
         uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
-        uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+        const uint32_t cp0 = SPECK > 1 ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        uint32_t wd = (cp0 << 14) | (uint32_t)p;
         uint32_t tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
+        const uint32_t v_own = v, wd_own = wd;
         warp_argmax(v, wd);
+        if (SPECK > 1) {
+            const uint32_t sec = __reduce_max_sync(0xffffffffu, wd_own == wd ? 0u : v_own);
+            if (lane == j) bval2 = sec;
+        }
         if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
     }
 
@@ -355,106 +378,235 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         }
         cooperative_groups::this_cluster().sync();   // every CTA of the cluster runs and has its barriers initialised
     }
-    for (int it = first_it; it < m; ++it) {
-        bool act = false;
-        if (lane < BPW) {
-            if (prune) {
-                float lb = bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, x1, y1, z1);
-                act = lb < bmaxt;
-            } else {
-                act = ((lane * NW + w) << 5) < n;
+    if constexpr (SPECK > 1) {
+        const uint32_t scp_s = (uint32_t)__cvta_generic_to_shared(scp);
+        float qx[SPECK], qy[SPECK], qz[SPECK];   // samples selected in the previous round, their updates still pending
+        int A = 1;
+        qx[0] = x1; qy[0] = y1; qz[0] = z1;
+#pragma unroll
+        for (int i = 1; i < SPECK; ++i) { qx[i] = x1; qy[i] = y1; qz[i] = z1; }
+        // one pass over the buckets a pending sample can change: min-distances, bucket maximum / second / bound
+        auto update_pass = [&](int na) {
+            bool act = false;
+            if (lane < BPW) {
+                float lb = bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, qx[0], qy[0], qz[0]);
+#pragma unroll
+                for (int i = 1; i < SPECK; ++i)
+                    if (i < na) lb = fminf(lb, bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, qx[i], qy[i], qz[i]));
+                act = prune ? (lb < bmaxt) : (((lane * NW + w) << 5) < n);
             }
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, act);
-        // Visit only the active buckets.  The min-distances live in registers, so the bucket number must be a
-        // compile-time constant inside the body: a warp-uniform switch (one indirect branch per active bucket)
-        // instead of BPW predicated copies of the body that every iteration would have to walk through.
-        auto visit = [&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            if constexpr (j < BPW) {
-                const int p = ((j * NW + w) << 5) | lane;
-                constexpr uint32_t off = (uint32_t)j * NW * 32u * 4u;
-                float d = sqdist(lds_f32(sx_s + lane_off + off), lds_f32(sy_s + lane_off + off), lds_f32(sz_s + lane_off + off), x1, y1, z1);
-                float t = fminf(d, temp[j]);
-                if (p >= n) t = -INFINITY;
-                temp[j] = t;
-                float val = MODE == FPS_S ? sfps_key(t, wt[MODE == FPS_S ? j : 0]) : t;
-                uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
-                uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
-                uint32_t tm;
-                if (MODE == FPS_S) tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
-                warp_argmax(v, wd);
-                if (MODE == FPS_D) tm = v;
-                if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+            unsigned mask = __ballot_sync(0xffffffffu, act);
+            auto visit = [&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                if constexpr (j < BPW) {
+                    const int p = ((j * NW + w) << 5) | lane;
+                    constexpr uint32_t off = (uint32_t)j * NW * 32u * 4u;
+                    const float x = lds_f32(sx_s + lane_off + off), y = lds_f32(sy_s + lane_off + off), z = lds_f32(sz_s + lane_off + off);
+                    unsigned short cps;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cps) : "r"(scp_s + (lane_off >> 1) + (off >> 1)));
+                    float t = fminf(sqdist(x, y, z, qx[0], qy[0], qz[0]), temp[j]);
+#pragma unroll
+                    for (int i = 1; i < SPECK; ++i)
+                        if (i < na) t = fminf(sqdist(x, y, z, qx[i], qy[i], qz[i]), t);
+                    if (p >= n) t = -INFINITY;
+                    temp[j] = t;
+                    const uint32_t v_own = (p < n && t == t) ? f2ord(t) : 0u;
+                    const uint32_t wd_own = ((uint32_t)cps << 14) | (uint32_t)p;
+                    uint32_t v = v_own, wd = wd_own;
+                    warp_argmax(v, wd);
+                    const uint32_t sec = __reduce_max_sync(0xffffffffu, wd_own == wd ? 0u : v_own);
+                    if (lane == j) { bval = v; bword = wd; bmaxt = v ? ord2f(v) : -INFINITY; bval2 = sec; }
+                }
+            };
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                switch (j) {
+#define DE6D_FPS_CASE(J) case J: visit(std::integral_constant<int, J>{}); break;
+                    DE6D_FPS_CASE(0) DE6D_FPS_CASE(1) DE6D_FPS_CASE(2) DE6D_FPS_CASE(3) DE6D_FPS_CASE(4) DE6D_FPS_CASE(5)
+                    DE6D_FPS_CASE(6) DE6D_FPS_CASE(7) DE6D_FPS_CASE(8) DE6D_FPS_CASE(9) DE6D_FPS_CASE(10) DE6D_FPS_CASE(11)
+                    DE6D_FPS_CASE(12) DE6D_FPS_CASE(13) DE6D_FPS_CASE(14) DE6D_FPS_CASE(15) DE6D_FPS_CASE(16) DE6D_FPS_CASE(17)
+                    DE6D_FPS_CASE(18) DE6D_FPS_CASE(19) DE6D_FPS_CASE(20) DE6D_FPS_CASE(21) DE6D_FPS_CASE(22) DE6D_FPS_CASE(23)
+                    DE6D_FPS_CASE(24) DE6D_FPS_CASE(25) DE6D_FPS_CASE(26) DE6D_FPS_CASE(27) DE6D_FPS_CASE(28) DE6D_FPS_CASE(29)
+                    DE6D_FPS_CASE(30) DE6D_FPS_CASE(31)
+#undef DE6D_FPS_CASE
+                    default: break;
+                }
             }
         };
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            switch (j) {
-#define DE6D_FPS_CASE(J) case J: visit(std::integral_constant<int, J>{}); break;
-                DE6D_FPS_CASE(0) DE6D_FPS_CASE(1) DE6D_FPS_CASE(2) DE6D_FPS_CASE(3) DE6D_FPS_CASE(4) DE6D_FPS_CASE(5)
-                DE6D_FPS_CASE(6) DE6D_FPS_CASE(7) DE6D_FPS_CASE(8) DE6D_FPS_CASE(9) DE6D_FPS_CASE(10) DE6D_FPS_CASE(11)
-                DE6D_FPS_CASE(12) DE6D_FPS_CASE(13) DE6D_FPS_CASE(14) DE6D_FPS_CASE(15) DE6D_FPS_CASE(16) DE6D_FPS_CASE(17)
-                DE6D_FPS_CASE(18) DE6D_FPS_CASE(19) DE6D_FPS_CASE(20) DE6D_FPS_CASE(21) DE6D_FPS_CASE(22) DE6D_FPS_CASE(23)
-                DE6D_FPS_CASE(24) DE6D_FPS_CASE(25) DE6D_FPS_CASE(26) DE6D_FPS_CASE(27) DE6D_FPS_CASE(28) DE6D_FPS_CASE(29)
-                DE6D_FPS_CASE(30) DE6D_FPS_CASE(31)
-#undef DE6D_FPS_CASE
-                default: break;
+        const uint32_t wq_s = (uint32_t)__cvta_generic_to_shared(wq), bq_s = (uint32_t)__cvta_generic_to_shared(bq);
+        int it = first_it;
+        while (it < m) {
+            update_pass(A);
+            // ---- this warp's two best bucket maxima + the largest value it does not report ----
+            uint32_t a1 = bval, b1 = bword;
+            warp_argmax(a1, b1);
+            const bool is1 = (bword == b1) && (b1 != 0xffffffffu);
+            uint32_t a2 = is1 ? 0u : bval, b2 = is1 ? 0xffffffffu : bword;
+            warp_argmax(a2, b2);
+            const bool is2 = !is1 && (bword == b2) && (b2 != 0xffffffffu);
+            const uint32_t bnd = __reduce_max_sync(0xffffffffu, max((is1 || is2) ? 0u : bval, bval2));
+            if (lane == 0) {
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wq_s + (uint32_t)(par * NW + w) * 16u), "r"(a1), "r"(b1), "r"(a2), "r"(b2) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(bq_s + (uint32_t)(par * NW + w) * 4u), "r"(bnd) : "memory");
+            }
+            __syncthreads();
+            // ---- global top-SPECK of the 2 * NW reported maxima, and the global bound ----
+            uint32_t ev = 0u, ew = 0xffffffffu, eb = 0u;
+            if (lane < 2 * NW) {
+                const uint2 e = lds_u32x2(wq_s + (uint32_t)(par * NW + (lane >> 1)) * 16u + (uint32_t)(lane & 1) * 8u);
+                ev = e.x; ew = e.y;
+            }
+            if (lane < NW) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(eb) : "r"(bq_s + (uint32_t)(par * NW + lane) * 4u));
+            par ^= 1;
+            const uint32_t bound = __reduce_max_sync(0xffffffffu, eb);
+            uint32_t cv[SPECK], cw[SPECK];
+#pragma unroll
+            for (int j = 0; j < SPECK; ++j) {
+                uint32_t a = ev, b = ew;
+                warp_argmax(a, b);
+                cv[j] = a; cw[j] = b;
+                if (ew == b) { ev = 0u; ew = 0xffffffffu; }
+            }
+            // ---- accept the longest prefix that is provably the reference sequence ----
+            const int limit = min(SPECK, m - it);
+            if (cv[0] > ORD_M1) {
+                const uint32_t p0 = cw[0] & 0x3fffu;
+                qx[0] = lds_f32(sx_s + p0 * 4u); qy[0] = lds_f32(sy_s + p0 * 4u); qz[0] = lds_f32(sz_s + p0 * 4u);
+                A = 1;
+                bool go = true;
+#pragma unroll
+                for (int j = 1; j < SPECK; ++j) {
+                    if (go && j < limit && cv[j] > bound && ord2f(cv[j]) > 0.f) {
+                        const uint32_t pj = cw[j] & 0x3fffu;
+                        const float cx = lds_f32(sx_s + pj * 4u), cy = lds_f32(sy_s + pj * 4u), cz = lds_f32(sz_s + pj * 4u);
+                        const float tj = ord2f(cv[j]);
+                        bool ok = true;
+#pragma unroll
+                        for (int i = 0; i < j; ++i) ok = ok && !(sqdist(cx, cy, cz, qx[i], qy[i], qz[i]) < tj);
+                        if (ok) { qx[j] = cx; qy[j] = cy; qz[j] = cz; A = j + 1; }
+                        else go = false;
+                    } else {
+                        go = false;
+                    }
+                }
+                if (tid == 0) {
+#pragma unroll
+                    for (int j = 0; j < SPECK; ++j)
+                        if (j < A) idxs[it + j] = (int)index_of_cprio(cw[j] >> 14, log2B, ibits);
+                }
+            } else {   // nothing exceeds -1: the reference selects index 0
+                qx[0] = lds_f32(sx_s + pos0 * 4u); qy[0] = lds_f32(sy_s + pos0 * 4u); qz[0] = lds_f32(sz_s + pos0 * 4u);
+                A = 1;
+                if (tid == 0) idxs[it] = 0;
+            }
+            it += A;
+        }
+        // the reference applies every sample's update except the last one's: catch up on the final round
+        if (A > 1) update_pass(A - 1);
+    } else {
+    for (int it = first_it; it < m; ++it) {
+            bool act = false;
+            if (lane < BPW) {
+                if (prune) {
+                    float lb = bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, x1, y1, z1);
+                    act = lb < bmaxt;
+                } else {
+                    act = ((lane * NW + w) << 5) < n;
+                }
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, act);
+            // Visit only the active buckets.  The min-distances live in registers, so the bucket number must be a
+            // compile-time constant inside the body: a warp-uniform switch (one indirect branch per active bucket)
+            // instead of BPW predicated copies of the body that every iteration would have to walk through.
+            auto visit = [&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                if constexpr (j < BPW) {
+                    const int p = ((j * NW + w) << 5) | lane;
+                    constexpr uint32_t off = (uint32_t)j * NW * 32u * 4u;
+                    float d = sqdist(lds_f32(sx_s + lane_off + off), lds_f32(sy_s + lane_off + off), lds_f32(sz_s + lane_off + off), x1, y1, z1);
+                    float t = fminf(d, temp[j]);
+                    if (p >= n) t = -INFINITY;
+                    temp[j] = t;
+                    float val = MODE == FPS_S ? sfps_key(t, wt[MODE == FPS_S ? j : 0]) : t;
+                    uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
+                    uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+                    uint32_t tm;
+                    if (MODE == FPS_S) tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
+                    warp_argmax(v, wd);
+                    if (MODE == FPS_D) tm = v;
+                    if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+                }
+            };
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                switch (j) {
+    #define DE6D_FPS_CASE(J) case J: visit(std::integral_constant<int, J>{}); break;
+                    DE6D_FPS_CASE(0) DE6D_FPS_CASE(1) DE6D_FPS_CASE(2) DE6D_FPS_CASE(3) DE6D_FPS_CASE(4) DE6D_FPS_CASE(5)
+                    DE6D_FPS_CASE(6) DE6D_FPS_CASE(7) DE6D_FPS_CASE(8) DE6D_FPS_CASE(9) DE6D_FPS_CASE(10) DE6D_FPS_CASE(11)
+                    DE6D_FPS_CASE(12) DE6D_FPS_CASE(13) DE6D_FPS_CASE(14) DE6D_FPS_CASE(15) DE6D_FPS_CASE(16) DE6D_FPS_CASE(17)
+                    DE6D_FPS_CASE(18) DE6D_FPS_CASE(19) DE6D_FPS_CASE(20) DE6D_FPS_CASE(21) DE6D_FPS_CASE(22) DE6D_FPS_CASE(23)
+                    DE6D_FPS_CASE(24) DE6D_FPS_CASE(25) DE6D_FPS_CASE(26) DE6D_FPS_CASE(27) DE6D_FPS_CASE(28) DE6D_FPS_CASE(29)
+                    DE6D_FPS_CASE(30) DE6D_FPS_CASE(31)
+    #undef DE6D_FPS_CASE
+                    default: break;
+                }
+            }
+            uint32_t v = bval, wd = bword;
+            warp_argmax(v, wd);
+            if (lane == 0) sts_u32x2(wbuf_s + (uint32_t)(par * NW + w) * 8u, v, wd);
+            __syncthreads();
+            uint2 e = make_uint2(0u, 0xffffffffu);
+            if (lane < NW) e = lds_u32x2(wbuf_s + (uint32_t)(par * NW + lane) * 8u);
+            par ^= 1;
+            v = e.x; wd = e.y;
+            warp_argmax(v, wd);
+            // reference candidate rule: a value must exceed -1 to be selected (best starts at -1, index 0);
+            // ORD_M1 = f2ord(-1.0f), and NaN keys were mapped to 0
+            const bool found = v > ORD_M1;
+            const uint32_t pos = found ? (wd & 0x3fffu) : pos0;
+            x1 = lds_f32(sx_s + pos * 4u); y1 = lds_f32(sy_s + pos * 4u); z1 = lds_f32(sz_s + pos * 4u);
+            if (!CL) {
+                if (tid == 0) idxs[it] = found ? (int)index_of_cprio(wd >> 14, log2B, ibits) : 0;
+            } else {
+                // this CTA's candidate -> every CTA of the cluster; global priority = (bit-reversed slot, k / B) with the
+                // slice offset added to the k / B field (the slice start is a multiple of B, so the slot is unchanged)
+                const uint32_t cp = wd >> 14;
+                const uint32_t gprio = found ? (((cp >> ibits) << 22) | ((cp & ((1u << ibits) - 1u)) + (uint32_t)(lo >> log2B))) : 0xffffffffu;
+                const uint32_t gv = found ? v : 0u;
+                const int rpar = (it - first_it) & 1;
+                if (tid == 0) fps_mbar_expect_tx(mbar_s + 8u * rpar, (uint32_t)S * 20u);
+                if (w == 0 && lane < S) {
+                    const uint32_t row = fps_mapa(rows_s + (uint32_t)((rpar * 8 + rank) * 8) * 4u, (uint32_t)lane);
+                    const uint32_t rbar = fps_mapa(mbar_s + 8u * rpar, (uint32_t)lane);
+                    fps_st_async(row, gv, rbar);
+                    fps_st_async(row + 4u, gprio, rbar);
+                    fps_st_async(row + 8u, __float_as_uint(x1), rbar);
+                    fps_st_async(row + 12u, __float_as_uint(y1), rbar);
+                    fps_st_async(row + 16u, __float_as_uint(z1), rbar);
+                }
+                fps_mbar_wait(mbar_s + 8u * rpar, (phases >> rpar) & 1u);
+                phases ^= 1u << rpar;
+                uint32_t rv = 0u, rp = 0xffffffffu;
+                float rx = 0.f, ry = 0.f, rz = 0.f;
+                if (lane < S) {
+                    const uint32_t *r = rows + (rpar * 8 + lane) * 8;
+                    rv = r[0]; rp = r[1]; rx = __uint_as_float(r[2]); ry = __uint_as_float(r[3]); rz = __uint_as_float(r[4]);
+                }
+                uint32_t bv2 = rv, bp2 = rp;
+                warp_argmax(bv2, bp2);
+                if (bv2 > ORD_M1) {
+                    const int src = __ffs(__ballot_sync(0xffffffffu, rv == bv2 && rp == bp2)) - 1;
+                    x1 = __shfl_sync(0xffffffffu, rx, src); y1 = __shfl_sync(0xffffffffu, ry, src); z1 = __shfl_sync(0xffffffffu, rz, src);
+                    if (rank == 0 && tid == 0) idxs[it] = (int)fps_prio_to_index(bp2, (uint32_t)log2B);
+                } else {   // the reference falls back to index 0 when no value exceeds -1
+                    x1 = gx0; y1 = gy0; z1 = gz0;
+                    if (rank == 0 && tid == 0) idxs[it] = 0;
+                }
             }
         }
-        uint32_t v = bval, wd = bword;
-        warp_argmax(v, wd);
-        if (lane == 0) sts_u32x2(wbuf_s + (uint32_t)(par * NW + w) * 8u, v, wd);
-        __syncthreads();
-        uint2 e = make_uint2(0u, 0xffffffffu);
-        if (lane < NW) e = lds_u32x2(wbuf_s + (uint32_t)(par * NW + lane) * 8u);
-        par ^= 1;
-        v = e.x; wd = e.y;
-        warp_argmax(v, wd);
-        // reference candidate rule: a value must exceed -1 to be selected (best starts at -1, index 0);
-        // ORD_M1 = f2ord(-1.0f), and NaN keys were mapped to 0
-        const bool found = v > ORD_M1;
-        const uint32_t pos = found ? (wd & 0x3fffu) : pos0;
-        x1 = lds_f32(sx_s + pos * 4u); y1 = lds_f32(sy_s + pos * 4u); z1 = lds_f32(sz_s + pos * 4u);
-        if (!CL) {
-            if (tid == 0) idxs[it] = found ? (int)index_of_cprio(wd >> 14, log2B, ibits) : 0;
-        } else {
-            // this CTA's candidate -> every CTA of the cluster; global priority = (bit-reversed slot, k / B) with the
-            // slice offset added to the k / B field (the slice start is a multiple of B, so the slot is unchanged)
-            const uint32_t cp = wd >> 14;
-            const uint32_t gprio = found ? (((cp >> ibits) << 22) | ((cp & ((1u << ibits) - 1u)) + (uint32_t)(lo >> log2B))) : 0xffffffffu;
-            const uint32_t gv = found ? v : 0u;
-            const int rpar = (it - first_it) & 1;
-            if (tid == 0) fps_mbar_expect_tx(mbar_s + 8u * rpar, (uint32_t)S * 20u);
-            if (w == 0 && lane < S) {
-                const uint32_t row = fps_mapa(rows_s + (uint32_t)((rpar * 8 + rank) * 8) * 4u, (uint32_t)lane);
-                const uint32_t rbar = fps_mapa(mbar_s + 8u * rpar, (uint32_t)lane);
-                fps_st_async(row, gv, rbar);
-                fps_st_async(row + 4u, gprio, rbar);
-                fps_st_async(row + 8u, __float_as_uint(x1), rbar);
-                fps_st_async(row + 12u, __float_as_uint(y1), rbar);
-                fps_st_async(row + 16u, __float_as_uint(z1), rbar);
-            }
-            fps_mbar_wait(mbar_s + 8u * rpar, (phases >> rpar) & 1u);
-            phases ^= 1u << rpar;
-            uint32_t rv = 0u, rp = 0xffffffffu;
-            float rx = 0.f, ry = 0.f, rz = 0.f;
-            if (lane < S) {
-                const uint32_t *r = rows + (rpar * 8 + lane) * 8;
-                rv = r[0]; rp = r[1]; rx = __uint_as_float(r[2]); ry = __uint_as_float(r[3]); rz = __uint_as_float(r[4]);
-            }
-            uint32_t bv2 = rv, bp2 = rp;
-            warp_argmax(bv2, bp2);
-            if (bv2 > ORD_M1) {
-                const int src = __ffs(__ballot_sync(0xffffffffu, rv == bv2 && rp == bp2)) - 1;
-                x1 = __shfl_sync(0xffffffffu, rx, src); y1 = __shfl_sync(0xffffffffu, ry, src); z1 = __shfl_sync(0xffffffffu, rz, src);
-                if (rank == 0 && tid == 0) idxs[it] = (int)fps_prio_to_index(bp2, (uint32_t)log2B);
-            } else {   // the reference falls back to index 0 when no value exceeds -1
-                x1 = gx0; y1 = gy0; z1 = gz0;
-                if (rank == 0 && tid == 0) idxs[it] = 0;
-            }
-        }
+    
     }
 
     // ---------------- write the running min-distances back (temp is an in/out tensor of the op) ---------
@@ -462,7 +614,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     for (int j = 0; j < BPW; ++j) {
         const int p = ((j * NW + w) << 5) | lane;
         if (p < n) {
-            uint32_t cp = (cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            uint32_t cp = SPECK > 1 ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
             temp_g[index_of_cprio(cp, log2B, ibits)] = temp[j];
         }
     }
@@ -610,14 +762,15 @@ static int ref_log2_block(int n) {  // opt_n_threads (cuda_utils.h:10-14), same 
     return p;
 }
 
-template <int MODE, int NW, int BPW, bool PRUNE>
+template <int MODE, int NW, int BPW, bool PRUNE, int SPECK = 1>
 static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float *xyz, const float *w, float *temp,
                          int *idx, cudaStream_t s) {
     constexpr int CAP = NW * BPW * 32;
-    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16;
+    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16 +
+                  2 * NW * 16 + 2 * NW * 4 + (SPECK > 1 ? (size_t)CAP * 2 : 0) + 16;
     static unsigned long long devs = 0;
-    if (int rc = de6d_ensure_smem(fps_bucket_kernel<MODE, NW, BPW, PRUNE>, (int)smem, devs, "fps smem attribute")) return rc;
-    fps_bucket_kernel<MODE, NW, BPW, PRUNE><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
+    if (int rc = de6d_ensure_smem(fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK>, (int)smem, devs, "fps smem attribute")) return rc;
+    fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
     DE6D_CHECK_LAUNCH("fps_bucket_kernel");
     return DE6D_OK;
 }
@@ -626,7 +779,7 @@ static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float 
 static int launch_bucket_cluster(int b, int n, int m, const float *xyz, float *temp, int *idx, cudaStream_t s) {
     constexpr int NW = 16, BPW = 32, CAP = NW * BPW * 32;
     const int S = (n + CAP - 1) / CAP;
-    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16;
+    size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16 + 2 * NW * 20 + 16;
     auto kern = fps_bucket_kernel<FPS_D, NW, BPW, true, true>;
     static unsigned long long devs = 0;
     if (int rc = de6d_ensure_smem(kern, (int)smem, devs, "fps cluster smem attribute")) return rc;
@@ -665,7 +818,14 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, f
         if (n <= 4096) return launch_bucket<MODE, 32, 4, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
         return launch_bucket<MODE, 32, 16, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
     }
-    if (n <= 16384 && impl != 2 && log2B + ibits <= 14) {
+    if constexpr (MODE == FPS_D) {   // default D-FPS: pruned buckets + up to 4 samples per barrier round
+        if (n <= 16384 && impl == 0 && log2B + ibits <= 14) {
+            if (n <= 1024) return launch_bucket<MODE, 8, 4, true, 4>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+            if (n <= 4096) return launch_bucket<MODE, 16, 8, true, 4>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+            return launch_bucket<MODE, 16, 32, true, 4>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+        }
+    }
+    if (n <= 16384 && impl != 2 && log2B + ibits <= 14) {   // impl 4 (and S-FPS): one sample per round
         if (n <= 1024)
             return prune ? launch_bucket<MODE, 8, 4, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s)
                          : launch_bucket<MODE, 8, 4, false>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);

@@ -56,7 +56,7 @@ def _fps_impl(xyz, m, impl, weights=None):
 # ------------------------------------------------------------------------------------------------ FPS
 @pytest.mark.parametrize("B,N,M,dup", [(2, 1000, 64, 0.1), (3, 2048, 300, 0.2), (1, 300, 299, 0.0), (2, 4096, 512, 0.05),
                                        (1, 33, 9, 0.3), (1, 1, 1, 0.0), (2, 5000, 200, 0.1), (1, 16383, 160, 0.1)])
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 4])
 def test_dfps_vs_oracle(orc, lib, B, N, M, dup, impl):
     xyz = synth.clouds(B, N, seed=N + M, dup_frac=dup)
     want_idx, want_temp = orc.furthest_point_sample(xyz, M, return_temp=True)
@@ -100,6 +100,34 @@ def test_dfps_cluster_stress_shape(lib):
     b, tb = _fps_impl(xyz, 16384, 2)
     np.testing.assert_array_equal(a, b); np.testing.assert_array_equal(ta, tb)
     assert len(set(a[0].tolist())) == 16384
+
+
+@pytest.mark.parametrize("N,M,kind", [(16384, 4096, "uniform"), (16384, 4096, "lidar"), (4096, 4096, "dup"), (3000, 1500, "grid"),
+                                      (512, 512, "uniform"), (16384, 600, "clusters")])
+def test_dfps_multi_sample_rounds_exact(orc, lib, N, M, kind):
+    """The default D-FPS kernel takes up to 4 samples per barrier round (speculation that is only accepted when it
+    provably equals the sequential choice).  Stress the acceptance logic: exhaustive sampling (M == N: rounds where
+    all remaining min-distances tie or are zero), heavy duplication, lattice clouds (masses of exact distance ties),
+    tight clusters (several top candidates inside one bucket / one warp), against the oracle and the
+    one-sample-per-round kernel, indices and written-back min-distances."""
+    rng = np.random.default_rng(N + M)
+    if kind == "uniform":
+        xyz = synth.clouds(2, N, seed=N)
+    elif kind == "lidar":
+        xyz = synth.lidar_clouds(2, N, seed=N)
+    elif kind == "dup":
+        xyz = synth.clouds(2, N, seed=N, dup_frac=0.6)
+    elif kind == "grid":
+        g = np.stack(np.meshgrid(np.arange(15), np.arange(20), np.arange(10), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+        xyz = np.stack([g[rng.permutation(N)] * np.float32(0.5), g[rng.permutation(N)] * np.float32(0.25)])
+    else:
+        centres = rng.uniform(0, 50, (12, 3))
+        xyz = (centres[rng.integers(0, 12, (2, N))] + rng.normal(0, 0.05, (2, N, 3))).astype(np.float32)
+    want, wtemp = orc.furthest_point_sample(xyz, M, return_temp=True)
+    for impl in (0, 4):
+        idx, temp = _fps_impl(xyz, M, impl)
+        np.testing.assert_array_equal(idx, want)
+        np.testing.assert_array_equal(temp, wtemp)
 
 
 def test_dfps_all_points_identical_and_caller_temp(orc, lib, ops):
@@ -565,7 +593,7 @@ def test_against_reference_cuda_golden(golden, ops, lib):
     g = golden
     for tag, m in (("a", 64), ("b", 128), ("c", 40), ("d", 256)):
         xyz = g["fps_%s_xyz" % tag]
-        for impl in (0, 1, 2):
+        for impl in (0, 1, 2, 4):
             idx, temp = _fps_impl(xyz, m, impl)
             np.testing.assert_array_equal(idx, g["fps_%s_idx" % tag]); np.testing.assert_array_equal(temp, g["fps_%s_temp" % tag])
             sidx, _ = _fps_impl(xyz, m, impl, weights=g["sfps_%s_w" % tag])
