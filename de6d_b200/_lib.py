@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libde6d_b200.so")
+LIB_PATH = os.environ.get("DE6D_LIB") or os.path.join(_HERE, "lib", "libde6d_b200.so")   # DE6D_LIB: development builds
 
 _p = C.c_void_p
 _i = C.c_int

@@ -818,8 +818,11 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, f
         if (n <= 4096) return launch_bucket<MODE, 32, 4, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
         return launch_bucket<MODE, 32, 16, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
     }
-    if constexpr (MODE == FPS_D) {   // default D-FPS: pruned buckets + up to 4 samples per barrier round
-        if (n <= 16384 && impl == 0 && log2B + ibits <= 14) {
+    if constexpr (MODE == FPS_D) {
+        // default D-FPS of large clouds: pruned buckets + up to 4 samples per barrier round (measured 4-10 % faster at
+        // 16384 points: 3.8 samples per round, but the per-sample instruction work, not the barrier count, bounds the
+        // kernel; at <= 4096 points the one-sample rounds are as fast).  impl 5 forces it at any size (tests).
+        if (n <= 16384 && ((impl == 0 && n > 4096) || impl == 5) && log2B + ibits <= 14) {
             if (n <= 1024) return launch_bucket<MODE, 8, 4, true, 4>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
             if (n <= 4096) return launch_bucket<MODE, 16, 8, true, 4>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
             return launch_bucket<MODE, 16, 32, true, 4>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);

@@ -56,7 +56,7 @@ def _fps_impl(xyz, m, impl, weights=None):
 # ------------------------------------------------------------------------------------------------ FPS
 @pytest.mark.parametrize("B,N,M,dup", [(2, 1000, 64, 0.1), (3, 2048, 300, 0.2), (1, 300, 299, 0.0), (2, 4096, 512, 0.05),
                                        (1, 33, 9, 0.3), (1, 1, 1, 0.0), (2, 5000, 200, 0.1), (1, 16383, 160, 0.1)])
-@pytest.mark.parametrize("impl", [0, 1, 2, 4])
+@pytest.mark.parametrize("impl", [0, 1, 2, 4, 5])
 def test_dfps_vs_oracle(orc, lib, B, N, M, dup, impl):
     xyz = synth.clouds(B, N, seed=N + M, dup_frac=dup)
     want_idx, want_temp = orc.furthest_point_sample(xyz, M, return_temp=True)
@@ -124,7 +124,7 @@ def test_dfps_multi_sample_rounds_exact(orc, lib, N, M, kind):
         centres = rng.uniform(0, 50, (12, 3))
         xyz = (centres[rng.integers(0, 12, (2, N))] + rng.normal(0, 0.05, (2, N, 3))).astype(np.float32)
     want, wtemp = orc.furthest_point_sample(xyz, M, return_temp=True)
-    for impl in (0, 4):
+    for impl in (0, 4, 5):     # automatic, one sample per round, multi-sample rounds forced at every size
         idx, temp = _fps_impl(xyz, M, impl)
         np.testing.assert_array_equal(idx, want)
         np.testing.assert_array_equal(temp, wtemp)
