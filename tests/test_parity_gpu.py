@@ -211,6 +211,32 @@ def test_fused_ffps_equals_matrix_path_and_oracle(orc, ops, B, N, C, M, layout):
         np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("C,M,kind", [(64, 4096, "dup"), (16, 2000, "lattice"), (32, 1500, "clusters"), (64, 512, "equal_features")])
+def test_fused_ffps_adversarial_ties(ops, C, M, kind):
+    """Fused F-FPS against the two-call path on inputs where ties decide: exhaustive sampling with massive duplication,
+    lattices (exact distance ties), tight clusters, identical feature vectors."""
+    pu = ops[0]
+    rng = np.random.default_rng(C + M)
+    N, B = 4096, 2
+    if kind == "dup":
+        xyz = synth.clouds(B, N, seed=3, dup_frac=0.5); feats = synth.features(B, C, N, seed=3)
+        src = rng.integers(0, N, N // 2); dst = rng.permutation(N)[: N // 2]
+        feats[:, :, dst] = feats[:, :, src]; xyz[:, dst] = xyz[:, src]
+    elif kind == "lattice":
+        g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+        xyz = np.stack([g[rng.permutation(N)], g[rng.permutation(N)] * np.float32(0.5)])
+        feats = np.round(synth.features(B, C, N, seed=4))
+    elif kind == "clusters":
+        ctr = rng.uniform(0, 40, (9, 3))
+        xyz = (ctr[rng.integers(0, 9, (B, N))] + rng.normal(0, 0.02, (B, N, 3))).astype(np.float32)
+        feats = (synth.features(B, C, N, seed=5) * 0.01).astype(np.float32)
+    else:
+        xyz = synth.clouds(B, N, seed=6); feats = np.ones((B, C, N), np.float32)
+    x, f = cu(xyz), cu(feats).permute(0, 2, 1)
+    two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
+    assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M), two)
+
+
 def test_fused_ffps_full_batch(ops):
     """Layer-2 shape of the chain at batch 16 (more clusters than fit at once: several waves)."""
     pu = ops[0]
