@@ -463,7 +463,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--pipeline", type=int, default=3, help="independent chains in flight (1 = strictly serial steps)")
+    ap.add_argument("--pipeline", type=int, default=6, help="independent chains in flight (1 = strictly serial steps)")
     ap.add_argument("--impl", default="de6d_b200", choices=["de6d_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
