@@ -71,8 +71,7 @@ def furthest_point_sample_matrix(matrix: torch.Tensor, npoint: int) -> torch.Ten
 
 
 @torch.no_grad()
-def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, gamma: float, npoint: int,
-                                   impl: int = 0) -> torch.Tensor:
+def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, gamma: float, npoint: int) -> torch.Tensor:
     """F-FPS without the (B, N, N) matrix: identical indices to
         furthest_point_sample_matrix(calc_dist_matrix_for_sampling(xyz, features, gamma), npoint)
     (the reference's call pair, pointnet2_modules.py:383-388).  xyz (B, N, 3), features (B, N, C) with any strides.
@@ -91,8 +90,8 @@ def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, ga
     else:
         assert features.is_cuda and features.dtype == torch.float32 and features.shape[:2] == (B, N)
         fptr, (sb, sn, sc) = features.data_ptr(), features.stride()
-    call("de6d_furthest_point_sampling_features_impl", B, N, C, npoint, xyz.data_ptr(), fptr, sb, sn, sc, float(gamma),
-         temp.data_ptr(), out.data_ptr(), int(impl), torch.cuda.current_stream().cuda_stream)   # impl pins a kernel variant (tests)
+    call("de6d_furthest_point_sampling_features", B, N, C, npoint, xyz.data_ptr(), fptr, sb, sn, sc, float(gamma),
+         temp.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     return out
 
 

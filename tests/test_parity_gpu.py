@@ -206,9 +206,6 @@ def test_fused_ffps_equals_matrix_path_and_oracle(orc, ops, B, N, C, M, layout):
     got = pu.furthest_point_sample_features(cu(xyz), dev_f, 0.7, M).cpu().numpy()
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(cu(xyz), dev_f, 0.7), M).cpu().numpy()
     np.testing.assert_array_equal(got, two)
-    if C == 64 and N <= 4096:      # both kernel variants: one CTA per SM (registers only) and two CTAs per SM (hybrid)
-        for impl in (1, 2):
-            np.testing.assert_array_equal(pu.furthest_point_sample_features(cu(xyz), dev_f, 0.7, M, impl=impl).cpu().numpy(), two)
     if N <= 1024:
         want = orc.furthest_point_sample_matrix(orc.calc_dist_matrix_for_sampling(xyz, feats_bnc, 0.7), M)
         np.testing.assert_array_equal(got, want)
@@ -238,8 +235,6 @@ def test_fused_ffps_adversarial_ties(ops, C, M, kind):
     x, f = cu(xyz), cu(feats).permute(0, 2, 1)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
     assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M), two)
-    if C == 64:
-        assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, impl=2), two)
 
 
 def test_fused_ffps_full_batch(ops):
@@ -247,10 +242,9 @@ def test_fused_ffps_full_batch(ops):
     pu = ops[0]
     xyz = cu(synth.clouds(16, 4096, seed=8))
     f = cu(synth.features(16, 64, 4096, seed=8)).permute(0, 2, 1)
-    got = pu.furthest_point_sample_features(xyz, f, 1.0, 512)              # batch 16: two CTAs per SM by default
+    got = pu.furthest_point_sample_features(xyz, f, 1.0, 512)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(xyz, f, 1.0), 512)
     assert torch.equal(got, two)
-    assert torch.equal(pu.furthest_point_sample_features(xyz, f, 1.0, 512, impl=1), two)
     assert all(len(set(r.tolist())) == 512 for r in got.cpu())
 
 
