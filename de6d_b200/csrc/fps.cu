@@ -124,15 +124,12 @@ __device__ __forceinline__ float bucket_lower_bound(float lox, float hix, float 
 // its bucket's maximum or behind a warp's two reported maxima could out-rank a candidate, so every bucket also
 // caches its second-best value and every warp reports the largest value it did not report: a candidate is only
 // accepted if it is strictly above that bound.  On FPS workloads ~3.5 of 4 candidates are accepted per round.
-// PPL = points per lane per bucket: a bucket is 32 * PPL Morton-consecutive points.  PPL = 2 halves the number of warps
-// (and with it the per-sample bookkeeping every warp repeats: lower bounds, arg-max, barrier) for the same cloud size.
-template <int MODE, int NW, int BPW, bool PRUNE, bool CL = false, int SPECK = 1, int PPL = 1>
+template <int MODE, int NW, int BPW, bool PRUNE, bool CL = false, int SPECK = 1>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict__ xyz_all,
                   const float *__restrict__ w_all, float *__restrict__ temp_all, int *__restrict__ idx_all) {
     constexpr int T = NW * 32;
-    constexpr int CAP = NW * BPW * 32 * PPL;
-    constexpr int NSLOT = BPW * PPL;      // 32-point slots per warp; slot j belongs to bucket j / PPL
+    constexpr int CAP = NW * BPW * 32;
     static_assert(BPW <= 32, "one owner lane per bucket");
     static_assert(!CL || MODE == FPS_D, "the cluster variant covers D-FPS");
     static_assert(SPECK == 1 || (MODE == FPS_D && !CL && PRUNE && 2 * NW <= 32), "multi-sample rounds: single-CTA pruned D-FPS");
@@ -162,8 +159,6 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     unsigned long long *sortbuf = reinterpret_cast<unsigned long long *>(smem_raw);  // aliases sx/sy
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    // sorted position of this lane's point in slot j: bucket (j / PPL) * NW + w covers 32 * PPL consecutive positions
-    auto slot_pos = [&](int j) { return ((((j / PPL) * NW + w) * PPL + (j % PPL)) << 5) | lane; };
     const float *xyz_cloud = xyz_all + (size_t)cloud * n_in * 3;
     const float *xyz = xyz_cloud + (size_t)lo * 3;
     const float *wts = MODE == FPS_S ? w_all + (size_t)cloud * n_in : nullptr;
@@ -174,7 +169,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     __syncthreads();
 
     // ---------------- prologue: order the cloud into buckets -----------------------------------------
-    uint32_t kk[NSLOT];  // original index of the point at (bucket j*NW+w, lane); 0xffffffff for padding
+    uint32_t kk[BPW];  // original index of the point at (bucket j*NW+w, lane); 0xffffffff for padding
     bool prune = PRUNE;
     if (PRUNE) {
         // cloud bounding box + finiteness
@@ -243,25 +238,25 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
             }
         }
 #pragma unroll
-        for (int j = 0; j < NSLOT; ++j) {
-            int p = slot_pos(j);
+        for (int j = 0; j < BPW; ++j) {
+            int p = ((j * NW + w) << 5) | lane;
             kk[j] = p < n ? (uint32_t)sortbuf[p] : 0xffffffffu;
         }
         __syncthreads();  // every item read before the coordinates overwrite the sort buffer
     } else {
 #pragma unroll
-        for (int j = 0; j < NSLOT; ++j) {
-            int p = slot_pos(j);
+        for (int j = 0; j < BPW; ++j) {
+            int p = ((j * NW + w) << 5) | lane;
             kk[j] = p < n ? (uint32_t)p : 0xffffffffu;
         }
     }
 
     // ---------------- load the cloud: coordinates -> smem, min-dist / priority / weight -> registers -------
-    float temp[NSLOT];
-    float wt[MODE == FPS_S ? NSLOT : 1];
-    uint32_t cpk[(NSLOT + 1) / 2];  // two 14-bit priorities per register
+    float temp[BPW];
+    float wt[MODE == FPS_S ? BPW : 1];
+    uint32_t cpk[(BPW + 1) / 2];  // two 14-bit priorities per register
 #pragma unroll
-    for (int j = 0; j < (NSLOT + 1) / 2; ++j) cpk[j] = 0;
+    for (int j = 0; j < (BPW + 1) / 2; ++j) cpk[j] = 0;
     // per-lane bucket state (lane j owns bucket j*NW+w)
     float blox = INFINITY, bhix = -INFINITY, bloy = INFINITY, bhiy = -INFINITY, bloz = INFINITY, bhiz = -INFINITY;
     float bmaxt = -INFINITY;      // largest min-distance inside the bucket (pruning bound)
@@ -269,8 +264,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     uint32_t bval2 = 0;                      // SPECK: second-best value of the bucket (hidden behind bval)
 
 #pragma unroll
-    for (int j = 0; j < NSLOT; ++j) {
-        const int p = slot_pos(j);
+    for (int j = 0; j < BPW; ++j) {
+        const int p = ((j * NW + w) << 5) | lane;
         const uint32_t k = kk[j];
         float x = 0.f, y = 0.f, z = 0.f, t0 = -INFINITY;
         uint32_t cp = 0x3fffu;
@@ -296,9 +291,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
             uint32_t a4 = __reduce_min_sync(0xffffffffu, valid ? f2ord(z) : 0xffffffffu);
             uint32_t a5 = __reduce_max_sync(0xffffffffu, valid ? f2ord(z) : 0u);
             uint32_t anyv = __ballot_sync(0xffffffffu, valid);
-            if (lane == j / PPL && anyv) {   // the bucket's box accumulates over its PPL slots
-                blox = fminf(blox, ord2f(a0)); bhix = fmaxf(bhix, ord2f(a1)); bloy = fminf(bloy, ord2f(a2));
-                bhiy = fmaxf(bhiy, ord2f(a3)); bloz = fminf(bloz, ord2f(a4)); bhiz = fmaxf(bhiz, ord2f(a5));
+            if (lane == j && anyv) {
+                blox = ord2f(a0); bhix = ord2f(a1); bloy = ord2f(a2); bhiy = ord2f(a3); bloz = ord2f(a4); bhiz = ord2f(a5);
             }
         }
     }
@@ -325,8 +319,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     } else {
         uint32_t v = 0, wd = 0xffffffffu;
 #pragma unroll
-        for (int j = 0; j < NSLOT; ++j) {
-            const int p = slot_pos(j);
+        for (int j = 0; j < BPW; ++j) {
+            const int p = ((j * NW + w) << 5) | lane;
             if (p < n) {
                 float val = wt[j];
                 uint32_t vv = (val == val) ? f2ord(val) : 0u;
@@ -351,36 +345,28 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
 
     // cached bucket arg-max from the caller's initial temp (normally 1e10 everywhere)
 #pragma unroll
-    for (int b = 0; b < BPW; ++b) {
-        uint32_t v = 0u, wd = 0xffffffffu, tmv = 0u, vlo = 0u;   // this lane's best / the other values it holds
-#pragma unroll
-        for (int u = 0; u < PPL; ++u) {
-            const int j = b * PPL + u;
-            const int p = slot_pos(j);
-            const float t = temp[j];
-            const float val = MODE == FPS_S ? sfps_key(t, wt[MODE == FPS_S ? j : 0]) : t;
-            const uint32_t vv = (p < n && val == val) ? f2ord(val) : 0u;
-            const uint32_t cp0 = SPECK > 1 ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
-            const uint32_t ww = (cp0 << 14) | (uint32_t)p;
-            tmv = max(tmv, (p < n) ? f2ord(t) : 0u);
-            if (vv > v || (vv == v && ww < wd)) { vlo = max(vlo, v); v = vv; wd = ww; }
-            else vlo = max(vlo, vv);
-        }
-        const uint32_t tm = __reduce_max_sync(0xffffffffu, tmv);
+    for (int j = 0; j < BPW; ++j) {
+        const int p = ((j * NW + w) << 5) | lane;
+        float t = temp[j];
+        float val = MODE == FPS_S ? sfps_key(t, wt[j]) : t;
+        uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
+        const uint32_t cp0 = SPECK > 1 ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        uint32_t wd = (cp0 << 14) | (uint32_t)p;
+        uint32_t tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
         const uint32_t v_own = v, wd_own = wd;
         warp_argmax(v, wd);
         if (SPECK > 1) {
-            const uint32_t sec = __reduce_max_sync(0xffffffffu, wd_own == wd ? vlo : v_own);
-            if (lane == b) bval2 = sec;
+            const uint32_t sec = __reduce_max_sync(0xffffffffu, wd_own == wd ? 0u : v_own);
+            if (lane == j) bval2 = sec;
         }
-        if (lane == b) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+        if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
     }
 
     // ---------------- main loop: one selected point per iteration ------------------------------------------
     const uint32_t sx_s = (uint32_t)__cvta_generic_to_shared(sx), sy_s = (uint32_t)__cvta_generic_to_shared(sy),
                    sz_s = (uint32_t)__cvta_generic_to_shared(sz), wbuf_s = (uint32_t)__cvta_generic_to_shared(wbuf);
     const uint32_t pos0 = (uint32_t)misc[0];
-    const uint32_t lane_off = (uint32_t)(w * 32 * PPL + lane) * 4u;
+    const uint32_t lane_off = (uint32_t)((w << 5) | lane) * 4u;
     constexpr uint32_t ORD_M1 = 0x407fffffu;   // f2ord(-1.0f)
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows), mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
     uint32_t phases = 0u;
@@ -407,37 +393,29 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
 #pragma unroll
                 for (int i = 1; i < SPECK; ++i)
                     if (i < na) lb = fminf(lb, bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, qx[i], qy[i], qz[i]));
-                act = prune ? (lb < bmaxt) : (((lane * NW + w) * 32 * PPL) < n);
+                act = prune ? (lb < bmaxt) : (((lane * NW + w) << 5) < n);
             }
             unsigned mask = __ballot_sync(0xffffffffu, act);
-            auto visit = [&](auto bc) {
-                constexpr int b = decltype(bc)::value;
-                if constexpr (b < BPW) {
-                    uint32_t v = 0u, wd = 0xffffffffu, vlo = 0u;
+            auto visit = [&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                if constexpr (j < BPW) {
+                    const int p = ((j * NW + w) << 5) | lane;
+                    constexpr uint32_t off = (uint32_t)j * NW * 32u * 4u;
+                    const float x = lds_f32(sx_s + lane_off + off), y = lds_f32(sy_s + lane_off + off), z = lds_f32(sz_s + lane_off + off);
+                    unsigned short cps;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cps) : "r"(scp_s + (lane_off >> 1) + (off >> 1)));
+                    float t = fminf(sqdist(x, y, z, qx[0], qy[0], qz[0]), temp[j]);
 #pragma unroll
-                    for (int u = 0; u < PPL; ++u) {
-                        constexpr int j0 = b * PPL;
-                        const int j = j0 + u;
-                        const int p = slot_pos(j);
-                        const uint32_t off = (uint32_t)(b * NW * 32 * PPL + u * 32) * 4u;
-                        const float x = lds_f32(sx_s + lane_off + off), y = lds_f32(sy_s + lane_off + off), z = lds_f32(sz_s + lane_off + off);
-                        unsigned short cps;
-                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cps) : "r"(scp_s + (lane_off >> 1) + (off >> 1)));
-                        float t = fminf(sqdist(x, y, z, qx[0], qy[0], qz[0]), temp[j]);
-#pragma unroll
-                        for (int i = 1; i < SPECK; ++i)
-                            if (i < na) t = fminf(sqdist(x, y, z, qx[i], qy[i], qz[i]), t);
-                        if (p >= n) t = -INFINITY;
-                        temp[j] = t;
-                        const uint32_t vv = (p < n && t == t) ? f2ord(t) : 0u;
-                        const uint32_t ww = ((uint32_t)cps << 14) | (uint32_t)p;
-                        if (vv > v || (vv == v && ww < wd)) { vlo = max(vlo, v); v = vv; wd = ww; }
-                        else vlo = max(vlo, vv);
-                    }
-                    const uint32_t v_own = v, wd_own = wd;
+                    for (int i = 1; i < SPECK; ++i)
+                        if (i < na) t = fminf(sqdist(x, y, z, qx[i], qy[i], qz[i]), t);
+                    if (p >= n) t = -INFINITY;
+                    temp[j] = t;
+                    const uint32_t v_own = (p < n && t == t) ? f2ord(t) : 0u;
+                    const uint32_t wd_own = ((uint32_t)cps << 14) | (uint32_t)p;
+                    uint32_t v = v_own, wd = wd_own;
                     warp_argmax(v, wd);
-                    const uint32_t sec = __reduce_max_sync(0xffffffffu, wd_own == wd ? vlo : v_own);
-                    if (lane == b) { bval = v; bword = wd; bmaxt = v ? ord2f(v) : -INFINITY; bval2 = sec; }
+                    const uint32_t sec = __reduce_max_sync(0xffffffffu, wd_own == wd ? 0u : v_own);
+                    if (lane == j) { bval = v; bword = wd; bmaxt = v ? ord2f(v) : -INFINITY; bval2 = sec; }
                 }
             };
             while (mask) {
@@ -534,38 +512,30 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                     float lb = bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, x1, y1, z1);
                     act = lb < bmaxt;
                 } else {
-                    act = ((lane * NW + w) * 32 * PPL) < n;
+                    act = ((lane * NW + w) << 5) < n;
                 }
             }
             unsigned mask = __ballot_sync(0xffffffffu, act);
             // Visit only the active buckets.  The min-distances live in registers, so the bucket number must be a
             // compile-time constant inside the body: a warp-uniform switch (one indirect branch per active bucket)
             // instead of BPW predicated copies of the body that every iteration would have to walk through.
-            auto visit = [&](auto bc) {
-                constexpr int b = decltype(bc)::value;
-                if constexpr (b < BPW) {
-                    uint32_t v = 0u, wd = 0xffffffffu, tmv = 0u;
-#pragma unroll
-                    for (int u = 0; u < PPL; ++u) {
-                        const int j = b * PPL + u;
-                        const int p = slot_pos(j);
-                        const uint32_t off = (uint32_t)(b * NW * 32 * PPL + u * 32) * 4u;
-                        float d = sqdist(lds_f32(sx_s + lane_off + off), lds_f32(sy_s + lane_off + off), lds_f32(sz_s + lane_off + off), x1, y1, z1);
-                        float t = fminf(d, temp[j]);
-                        if (p >= n) t = -INFINITY;
-                        temp[j] = t;
-                        const float val = MODE == FPS_S ? sfps_key(t, wt[MODE == FPS_S ? j : 0]) : t;
-                        const uint32_t vv = (p < n && val == val) ? f2ord(val) : 0u;
-                        const uint32_t cp0 = SPECK > 1 ? 0u : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
-                        const uint32_t ww = (cp0 << 14) | (uint32_t)p;
-                        if (MODE == FPS_S) tmv = max(tmv, (p < n) ? f2ord(t) : 0u);
-                        if (vv > v || (vv == v && ww < wd)) { v = vv; wd = ww; }
-                    }
-                    uint32_t tm = 0u;
-                    if (MODE == FPS_S) tm = __reduce_max_sync(0xffffffffu, tmv);
+            auto visit = [&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                if constexpr (j < BPW) {
+                    const int p = ((j * NW + w) << 5) | lane;
+                    constexpr uint32_t off = (uint32_t)j * NW * 32u * 4u;
+                    float d = sqdist(lds_f32(sx_s + lane_off + off), lds_f32(sy_s + lane_off + off), lds_f32(sz_s + lane_off + off), x1, y1, z1);
+                    float t = fminf(d, temp[j]);
+                    if (p >= n) t = -INFINITY;
+                    temp[j] = t;
+                    float val = MODE == FPS_S ? sfps_key(t, wt[MODE == FPS_S ? j : 0]) : t;
+                    uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
+                    uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+                    uint32_t tm;
+                    if (MODE == FPS_S) tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
                     warp_argmax(v, wd);
                     if (MODE == FPS_D) tm = v;
-                    if (lane == b) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+                    if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
                 }
             };
             while (mask) {
@@ -641,8 +611,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
 
     // ---------------- write the running min-distances back (temp is an in/out tensor of the op) ---------
 #pragma unroll
-    for (int j = 0; j < NSLOT; ++j) {
-        const int p = slot_pos(j);
+    for (int j = 0; j < BPW; ++j) {
+        const int p = ((j * NW + w) << 5) | lane;
         if (p < n) {
             uint32_t cp = SPECK > 1 ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
             temp_g[index_of_cprio(cp, log2B, ibits)] = temp[j];
@@ -792,15 +762,15 @@ static int ref_log2_block(int n) {  // opt_n_threads (cuda_utils.h:10-14), same 
     return p;
 }
 
-template <int MODE, int NW, int BPW, bool PRUNE, int SPECK = 1, int PPL = 1>
+template <int MODE, int NW, int BPW, bool PRUNE, int SPECK = 1>
 static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float *xyz, const float *w, float *temp,
                          int *idx, cudaStream_t s) {
-    constexpr int CAP = NW * BPW * 32 * PPL;
+    constexpr int CAP = NW * BPW * 32;
     size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16 +
                   2 * NW * 16 + 2 * NW * 4 + (SPECK > 1 ? (size_t)CAP * 2 : 0) + 16;
     static unsigned long long devs = 0;
-    if (int rc = de6d_ensure_smem(fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK, PPL>, (int)smem, devs, "fps smem attribute")) return rc;
-    fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK, PPL><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
+    if (int rc = de6d_ensure_smem(fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK>, (int)smem, devs, "fps smem attribute")) return rc;
+    fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
     DE6D_CHECK_LAUNCH("fps_bucket_kernel");
     return DE6D_OK;
 }
@@ -849,9 +819,6 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, f
         return launch_bucket<MODE, 32, 16, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
     }
     if constexpr (MODE == FPS_D) {
-        // experimental: 64-point buckets (two points per lane), half the warps
-        if (n > 4096 && n <= 16384 && impl == 6 && log2B + ibits <= 14) return launch_bucket<MODE, 8, 32, true, 4, 2>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
-        if (n > 4096 && n <= 16384 && impl == 7 && log2B + ibits <= 14) return launch_bucket<MODE, 8, 32, true, 1, 2>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
         // default D-FPS of large clouds: pruned buckets + up to 4 samples per barrier round (measured 4-10 % faster at
         // 16384 points: 3.8 samples per round, but the per-sample instruction work, not the barrier count, bounds the
         // kernel; at <= 4096 points the one-sample rounds are as fast).  impl 5 forces it at any size (tests).

@@ -37,14 +37,14 @@ for maker_name, maker in (("uniform", synth.clouds), ("lidar", synth.lidar_cloud
         temp = torch.empty((B, n), device="cuda")
         idx = torch.empty((B, m), dtype=torch.int32, device="cuda")
         res = {}
-        for impl in (0, 4, 6, 7):
+        for impl in (0, 4, 1):
             def run():
                 temp.fill_(1e10)
                 call("de6d_furthest_point_sampling_impl", B, n, m, xyz.data_ptr(), temp.data_ptr(), idx.data_ptr(), impl, s())
             t = timeit(run)
             res[impl] = idx.clone()
             print("D-FPS %-8s B=%d n=%5d m=%4d impl=%d : %8.3f ms" % (maker_name, B, n, m, impl, t), flush=True)
-        assert torch.equal(res[0], res[4]) and torch.equal(res[0], res[6]) and torch.equal(res[0], res[7])
+        assert torch.equal(res[0], res[4]) and torch.equal(res[0], res[1])
 
 xyz = cu(synth.clouds(B, 4096, seed=1))
 f = cu(synth.features(B, 64, 4096, seed=1)).permute(0, 2, 1)

@@ -124,7 +124,7 @@ def test_dfps_multi_sample_rounds_exact(orc, lib, N, M, kind):
         centres = rng.uniform(0, 50, (12, 3))
         xyz = (centres[rng.integers(0, 12, (2, N))] + rng.normal(0, 0.05, (2, N, 3))).astype(np.float32)
     want, wtemp = orc.furthest_point_sample(xyz, M, return_temp=True)
-    for impl in (0, 4, 5, 6, 7):   # automatic, one sample per round, multi-sample rounds forced, 64-point buckets (4 / 1 samples per round)
+    for impl in (0, 4, 5):     # automatic, one sample per round, multi-sample rounds forced at every size
         idx, temp = _fps_impl(xyz, M, impl)
         np.testing.assert_array_equal(idx, want)
         np.testing.assert_array_equal(temp, wtemp)
