@@ -205,9 +205,14 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
     const bool aligned = (ms % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const bool tma_ok = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    // channel rows per CTA: as many as fit in ~64 KB (three CTAs per SM hide the index-load latency better than one
+    // CTA with 192 KB: measured +3..10 % on B200, scripts/group_tune.py), at most 8, at least one if a row fits at all
     int G = (int)(smem_budget / ((size_t)n_pad * 4 + 1));
+    const int G64 = (int)((64 * 1024) / ((size_t)n_pad * 4 + 1));
+    if (G > 1 && G64 >= 1 && G > G64) G = G64;
+    if (G > 1 && G64 < 1) G = 1;
     if (G > c) G = c;
-    if (G > 16) G = 16;
+    if (G > 8) G = 8;
     bool staged = aligned && G >= 1 && ms >= 2ll * n;
     if (force_impl == 1) staged = false;
     if (force_impl == 2 && !(aligned && G >= 1)) return de6d_set_error(DE6D_ERR_INVALID, "group: staged kernel not applicable");
@@ -218,7 +223,7 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
         // enough CTAs to fill the machine, but each CTA should write >= ~2x what it stages
         long long min_chunk = (long long)n * 2;
         if (min_chunk < 4096) min_chunk = 4096;
-        long long want = ceil_div_ll(2 * 148, (long long)b * cgroups);
+        long long want = ceil_div_ll(8 * 148, (long long)b * cgroups);   // ~8 waves of CTAs: small tail
         long long chunks = want < 1 ? 1 : want;
         long long chunk = ceil_div_ll(ms, chunks);
         if (chunk < min_chunk) chunk = min_chunk;
