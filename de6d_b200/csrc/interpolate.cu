@@ -79,6 +79,53 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, 
     }
 }
 
+// Staged variant (the op is a 3-tap gather: HBM-bound if the taps do not each cost a 32-byte L2 sector): a CTA stages
+// G channel rows of one cloud in shared memory with TMA bulk copies, then every thread produces 4 consecutive outputs
+// per row from shared-memory taps -- idx / weight read as 128-bit vectors, 128-bit streaming stores.  Same FMA shape.
+constexpr int TI_THREADS = 256;
+
+__global__ void __launch_bounds__(TI_THREADS)
+three_interpolate_staged_kernel(int c, int m, int n, int G, int m_pad, int chunk, const float *__restrict__ points,
+                                const int *__restrict__ idx, const float *__restrict__ weight, float *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    float *rows = reinterpret_cast<float *>(smem_raw + 128);
+    const int bs = blockIdx.z;
+    const int c0 = blockIdx.y * G;
+    const int g_here = min(G, c - c0);
+    const float *src = points + ((size_t)bs * c + c0) * m;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)g_here * (uint32_t)m * 4u);
+        for (int g = 0; g < g_here; ++g) tma_bulk_g2s(rows + (size_t)g * m_pad, src + (size_t)g * m, (uint32_t)m * 4u, bar);
+    }
+    mbar_wait(bar, 0);
+
+    const int q0 = blockIdx.x * chunk, q1 = min(n, q0 + chunk);
+    const int *ix = idx + (size_t)bs * n * 3;
+    const float *wt = weight + (size_t)bs * n * 3;
+    float *dst = out + ((size_t)bs * c + c0) * n;
+    for (int q = q0 + 4 * threadIdx.x; q < q1; q += 4 * TI_THREADS) {   // n % 4 == 0 and chunk % 4 == 0 (host)
+        const int4 i0 = ldg_stream_int4(ix + (size_t)q * 3), i1 = ldg_stream_int4(ix + (size_t)q * 3 + 4), i2 = ldg_stream_int4(ix + (size_t)q * 3 + 8);
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wt + (size_t)q * 3)), w1 = __ldg(reinterpret_cast<const float4 *>(wt + (size_t)q * 3 + 4)),
+                     w2 = __ldg(reinterpret_cast<const float4 *>(wt + (size_t)q * 3 + 8));
+        const int k[12] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
+        const float ww[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+        for (int g = 0; g < g_here; ++g) {
+            const float *r = rows + (size_t)g * m_pad;
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                v[u] = __fmaf_rn(ww[3 * u + 2], r[k[3 * u + 2]], __fmaf_rn(ww[3 * u], r[k[3 * u]], __fmul_rn(ww[3 * u + 1], r[k[3 * u + 1]])));
+            stg_stream_float4(dst + (size_t)g * n + q, make_float4(v[0], v[1], v[2], v[3]));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ grad_out, const int *__restrict__ idx,
                               const float *__restrict__ weight, float *__restrict__ grad_points) {
@@ -125,6 +172,34 @@ extern "C" int de6d_three_interpolate(int b, int c, int m, int n, const float *p
     if (b == 0 || c == 0 || n == 0) return DE6D_OK;
     if (!points || !idx || !weight || !out) return de6d_set_error(DE6D_ERR_INVALID, "three_interpolate: null pointer");
     if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "three_interpolate: batch > 65535");
+    // staged kernel: rows fit in shared memory, everything 16-byte aligned, enough outputs per staged row
+    const int m_pad = (m + 3) & ~3;
+    int G = (int)((64 * 1024) / ((size_t)m_pad * 4 + 1));
+    if (G < 1 && (size_t)m_pad * 4 <= 200 * 1024) G = 1;
+    if (G > c) G = c;
+    if (G > 8) G = 8;
+    const bool aligned = (n % 4 == 0) && (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(weight) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (G >= 1 && aligned && n >= m / 2) {
+        const int cgroups = ceil_div(c, G);
+        long long chunks = ceil_div_ll(8 * 148, (long long)b * cgroups);
+        if (chunks < 1) chunks = 1;
+        long long chunk = ceil_div_ll(n, chunks);
+        long long min_chunk = (long long)m;          // write at least as much as is staged
+        if (min_chunk < 1024) min_chunk = 1024;
+        if (chunk < min_chunk) chunk = min_chunk;
+        chunk = (chunk + 3) & ~3ll;
+        chunks = ceil_div_ll(n, chunk);
+        const size_t smem = 128 + (size_t)G * m_pad * 4;
+        static unsigned long long devs = 0;
+        if (smem > 48 * 1024)
+            if (int rc = de6d_ensure_smem(three_interpolate_staged_kernel, 208 * 1024, devs, "three_interpolate smem attribute")) return rc;
+        dim3 grid((unsigned)chunks, cgroups, b);
+        three_interpolate_staged_kernel<<<grid, TI_THREADS, smem, stream>>>(c, m, n, G, m_pad, (int)chunk, points, idx, weight, out);
+        DE6D_CHECK_LAUNCH("three_interpolate_staged_kernel");
+        return DE6D_OK;
+    }
     dim3 grid(ceil_div(n, 256), ceil_div(c, TI_CPT), b);
     three_interpolate_kernel<<<grid, 256, 0, stream>>>(c, m, n, points, idx, weight, out);
     DE6D_CHECK_LAUNCH("three_interpolate_kernel");

@@ -474,6 +474,19 @@ def test_three_nn_interpolate_vs_oracle(orc, ops):
     np.testing.assert_array_equal(i2.cpu().numpy(), wi2); np.testing.assert_array_equal(d2.cpu().numpy(), wd2)
 
 
+@pytest.mark.parametrize("B,C,m,n", [(2, 19, 1100, 3000), (2, 5, 1101, 3001), (1, 64, 4096, 16384), (3, 3, 52, 200), (1, 70, 20000, 24000)])
+def test_three_interpolate_staged_and_direct_vs_oracle(orc, ops, B, C, m, n):
+    """three_interpolate: the TMA-staged kernel (aligned shapes, rows in shared memory) and the direct kernel
+    (unaligned shapes / rows too large) are both bit-identical to the oracle (the FMA shape is pinned)."""
+    pu = ops[0]
+    rng = np.random.default_rng(m + n)
+    feats = synth.features(B, C, m, seed=7)
+    idx = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w = rng.uniform(0, 1, (B, n, 3)).astype(np.float32)
+    out = pu.three_interpolate(cu(feats), cu(idx), cu(w)).cpu().numpy()
+    np.testing.assert_array_equal(out, orc.three_interpolate(feats, idx, w))
+
+
 # ------------------------------------------------------------------------------------------------ boxes
 def _near_threshold(iou, thr, eps=1e-5):
     return np.abs(iou - thr) < eps
