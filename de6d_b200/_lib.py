@@ -36,6 +36,7 @@ PROTOTYPES = {
     "de6d_group_concat": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "de6d_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
+    "de6d_three_nn_ex": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p],
     "de6d_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "de6d_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "de6d_boxes_overlap_bev": [_i, _p, _i, _p, _p, _p],

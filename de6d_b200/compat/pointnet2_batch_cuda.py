@@ -84,10 +84,12 @@ def furthest_point_sampling_weights_wrapper(b, n, m, xyz, weights, temp, idx):
     return 1
 
 
-def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
+def three_nn_wrapper(b, n, m, unknown, known, dist2, idx, impl=0):
     need(unknown, b * n * 3, "unknown"); need(known, b * m * 3, "known"); need(dist2, b * n * 3, "dist2"); need(idx, b * n * 3, "idx")
-    call("de6d_three_nn", b, n, m, dev(unknown, "unknown", f32), dev(known, "known", f32), dev(dist2, "dist2", f32),
-         dev(idx, "idx", i32), stream_ptr())
+    ws_bytes = int(load().de6d_ball_query_workspace_bytes(b, m)) if impl == 0 else 0   # grid over `known` for m >= 2048
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=known.device) if ws_bytes else None
+    call("de6d_three_nn_ex", impl, b, n, m, dev(unknown, "unknown", f32), dev(known, "known", f32), dev(dist2, "dist2", f32),
+         dev(idx, "idx", i32), None if ws is None else ws.data_ptr(), ws_bytes, stream_ptr())
     return 1
 
 

@@ -162,7 +162,7 @@ __device__ __forceinline__ int bqg_cell(float v, float o, float inv_c, int dim) 
 // END of each cell with atomicSub, which leaves exactly the cell starts behind.
 template <bool BIG>
 __global__ void __launch_bounds__(BQG_BUILD_T)
-bq_grid_build_kernel(int n, float r_abs, const float *__restrict__ xyz_all, unsigned char *__restrict__ ws_all,
+bq_grid_build_kernel(int n, float r_abs, int cell_cap, const float *__restrict__ xyz_all, unsigned char *__restrict__ ws_all,
                      size_t ws_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *cnt = reinterpret_cast<int *>(smem_raw);            // [BQG_CAP] histogram, then scatter cursors (!BIG)
@@ -210,19 +210,24 @@ bq_grid_build_kernel(int n, float r_abs, const float *__restrict__ xyz_all, unsi
         BQGridHeader h;
         h.valid = (n > 0 && !anybad && r_abs == r_abs && r_abs <= 1.0e30f) ? 1 : 0;
         float c = fmaxf(r_abs * 1.0002f, 1e-20f);
-        // smallest cell size >= the padded radius with at most BQG_CAP cells
+        // smallest cell size >= the padded radius with at most `cap` cells (cap <= CAP; three_nn asks for ~2 points per
+        // cell).  The search starts just below the cube root of volume / cap and grows by 10 % steps.
+        const int cap = min(max(cell_cap, 1), CAP);
         int dx = 1, dy = 1, dz = 1;
         if (h.valid) {
-            for (int it = 0; it < 400; ++it) {
+            const float vol = fmaxf(e[0], 1e-9f) * fmaxf(e[1], 1e-9f) * fmaxf(e[2], 1e-9f);
+            const float c0 = 0.7f * cbrtf(vol / (float)cap);
+            if (c0 == c0 && c0 < 1.0e30f) c = fmaxf(c, c0);
+            for (int it = 0; it < 800; ++it) {
                 const float fx = e[0] / c, fy = e[1] / c, fz = e[2] / c;
                 if (fx < 30000.f && fy < 30000.f && fz < 30000.f) {
                     dx = (int)fx + 1; dy = (int)fy + 1; dz = (int)fz + 1;
-                    if ((long long)dx * dy * dz <= CAP) break;
+                    if ((long long)dx * dy * dz <= cap) break;
                 }
-                c *= 1.2f;
+                c *= 1.1f;
                 dx = dy = dz = 1;
             }
-            if ((long long)dx * dy * dz > CAP) { dx = dy = dz = 1; }
+            if ((long long)dx * dy * dz > cap) { dx = dy = dz = 1; }
         }
         h.ox = l[0]; h.oy = l[1]; h.oz = l[2];
         h.inv_c = 1.0f / c;
@@ -436,6 +441,84 @@ bq_grid_query_kernel(int n, int m, float r_abs, float r2_in, float r2_out, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// three_nn through the same grid (interpolate_gpu.cu:16-59 scans all m known points per query).  The grid is built
+// over `known` with ~2 points per cell.  A query looks at the 3x3x3 block around its cell (then 5x5x5), keeping the
+// three best (distance, index) pairs in lexicographic order -- exactly what the reference's ascending scan with strict
+// '<' produces.  The result is final once the third distance is provably smaller than the distance to any point
+// outside the block: a point outside lies beyond a block face that is not on the grid boundary, i.e. at least `margin`
+// away along that axis (0.1 % + 1e-4 cell slack for the rounding of the cell assignment).  Otherwise the query falls
+// back to the reference's full scan.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nn3_insert(float d, int k, float &b1, float &b2, float &b3, int &i1, int &i2, int &i3) {
+    if (d < b1 || (d == b1 && k < i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+    else if (d < b2 || (d == b2 && k < i2)) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+    else if (d < b3 || (d == b3 && k < i3)) { b3 = d; i3 = k; }
+}
+
+__global__ void __launch_bounds__(256)
+three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
+                     const unsigned char *__restrict__ ws_all, size_t ws_stride, float *__restrict__ dist2, int *__restrict__ idx) {
+    const int bs = blockIdx.y;
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= n) return;
+    unknown += (size_t)bs * n * 3;
+    known += (size_t)bs * m * 3;
+    const unsigned char *ws = ws_all + (size_t)bs * ws_stride;
+    const BQGridHeader h = *reinterpret_cast<const BQGridHeader *>(ws);
+    const int *cell_start = reinterpret_cast<const int *>(ws + sizeof(BQGridHeader));
+    const float4 *sorted = reinterpret_cast<const float4 *>(ws + bqg_sorted_off(m));
+    const float ux = unknown[(size_t)q * 3], uy = unknown[(size_t)q * 3 + 1], uz = unknown[(size_t)q * 3 + 2];
+    float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+    int i1 = 0, i2 = 0, i3 = 0;
+    bool done = false;
+    if (h.valid && ux == ux && uy == uy && uz == uz) {
+        const float c = 1.0f / h.inv_c;
+        const int cx = bqg_cell(ux, h.ox, h.inv_c, h.dimx), cy = bqg_cell(uy, h.oy, h.inv_c, h.dimy), cz = bqg_cell(uz, h.oz, h.inv_c, h.dimz);
+        for (int R = 1; R <= 2 && !done; ++R) {
+            b1 = b2 = b3 = INFINITY; i1 = i2 = i3 = 0;
+            const int x0 = max(cx - R, 0), x1 = min(cx + R, h.dimx - 1), y0 = max(cy - R, 0), y1 = min(cy + R, h.dimy - 1);
+            const int z0 = max(cz - R, 0), z1 = min(cz + R, h.dimz - 1);
+            int found = 0;
+            for (int iz = z0; iz <= z1; ++iz)
+                for (int iy = y0; iy <= y1; ++iy) {
+                    const int row = (iz * h.dimy + iy) * h.dimx;
+                    const int s = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);
+                    for (int i = s; i < e; ++i) {
+                        const float4 p = __ldg(sorted + i);
+                        nn3_insert(sqdist(ux, uy, uz, p.x, p.y, p.z), __float_as_int(p.w), b1, b2, b3, i1, i2, i3);
+                    }
+                    found += e - s;
+                }
+            if (found >= 3) {
+                // distance from the query to the nearest block face behind which points can exist
+                float margin = INFINITY;
+                if (x0 > 0) margin = fminf(margin, ux - (h.ox + (float)x0 * c));
+                if (x1 < h.dimx - 1) margin = fminf(margin, (h.ox + (float)(x1 + 1) * c) - ux);
+                if (y0 > 0) margin = fminf(margin, uy - (h.oy + (float)y0 * c));
+                if (y1 < h.dimy - 1) margin = fminf(margin, (h.oy + (float)(y1 + 1) * c) - uy);
+                if (z0 > 0) margin = fminf(margin, uz - (h.oz + (float)z0 * c));
+                if (z1 < h.dimz - 1) margin = fminf(margin, (h.oz + (float)(z1 + 1) * c) - uz);
+                const float safe = margin * 0.999f - 1e-4f * c - 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+                done = (safe > 0.f) && (b3 < safe * safe * 0.999f);
+            }
+        }
+    }
+    if (!done) {   // the reference's scan
+        b1 = b2 = b3 = INFINITY; i1 = i2 = i3 = 0;
+        for (int k = 0; k < m; ++k) {
+            const float d = sqdist(ux, uy, uz, known[(size_t)k * 3], known[(size_t)k * 3 + 1], known[(size_t)k * 3 + 2]);
+            if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+            else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+            else if (d < b3) { b3 = d; i3 = k; }
+        }
+    }
+    float *dd = dist2 + ((size_t)bs * n + q) * 3;
+    int *ii = idx + ((size_t)bs * n + q) * 3;
+    dd[0] = b1; dd[1] = b2; dd[2] = b3;
+    ii[0] = i1; ii[1] = i2; ii[2] = i3;
+}
+
 constexpr int BQG_MIN_N = 2048;   // below this the brute-force kernel is already cheap
 
 template <int MODE>
@@ -469,8 +552,8 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
         if (int rc = de6d_ensure_smem(bq_grid_build_kernel<false>, BQG_CAP * 4, dev_build, "ball_query grid smem attribute")) return rc;
         if (int rc = de6d_ensure_smem(bq_grid_query_kernel<MODE>, 160 * 1024, dev_query, "ball_query query smem attribute")) return rc;
         const float r_abs = fabsf(r_out);
-        if (n > BQG_BIG_N) bq_grid_build_kernel<true><<<b, BQG_BUILD_T, 0, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
-        else bq_grid_build_kernel<false><<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, xyz, reinterpret_cast<unsigned char *>(ws), per);
+        if (n > BQG_BIG_N) bq_grid_build_kernel<true><<<b, BQG_BUILD_T, 0, s>>>(n, r_abs, BQG_CAP_BIG, xyz, reinterpret_cast<unsigned char *>(ws), per);
+        else bq_grid_build_kernel<false><<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, BQG_CAP, xyz, reinterpret_cast<unsigned char *>(ws), per);
         DE6D_CHECK_LAUNCH("bq_grid_build_kernel");
         double lim = 3.0 * sqrt((double)nsample * (double)n);
         if (lim < 1024.0) lim = 1024.0;
@@ -500,6 +583,35 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
 }  // namespace de6d
 
 using namespace de6d;
+
+// three_nn through the grid (called from interpolate.cu); workspace as for ball query over `known`, or NULL.
+int de6d_three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *workspace,
+                       size_t workspace_bytes, cudaStream_t s) {
+    const size_t per = bqg_ws_per_cloud(m), need = per * (size_t)b;
+    void *ws = workspace;
+    bool own = false;
+    if (!ws) {
+        cudaError_t e = cudaMallocAsync(&ws, need, s);
+        if (e != cudaSuccess) return de6d_set_cuda_error(e, "three_nn workspace");
+        own = true;
+    } else if (workspace_bytes < need) {
+        return de6d_set_error(DE6D_ERR_INVALID, "three_nn: workspace too small");
+    }
+    static unsigned long long dev_build = 0;
+    if (int rc = de6d_ensure_smem(bq_grid_build_kernel<false>, BQG_CAP * 4, dev_build, "three_nn grid smem attribute")) return rc;
+    const int cap = m / 2 > 1 ? m / 2 : 1;
+    if (m > BQG_BIG_N) bq_grid_build_kernel<true><<<b, BQG_BUILD_T, 0, s>>>(m, 0.f, cap, known, reinterpret_cast<unsigned char *>(ws), per);
+    else bq_grid_build_kernel<false><<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(m, 0.f, cap, known, reinterpret_cast<unsigned char *>(ws), per);
+    DE6D_CHECK_LAUNCH("bq_grid_build_kernel (three_nn)");
+    dim3 grid(ceil_div(n, 256), b);
+    three_nn_grid_kernel<<<grid, 256, 0, s>>>(n, m, unknown, known, reinterpret_cast<const unsigned char *>(ws), per, dist2, idx);
+    DE6D_CHECK_LAUNCH("three_nn_grid_kernel");
+    if (own) {
+        cudaError_t e = cudaFreeAsync(ws, s);
+        if (e != cudaSuccess) return de6d_set_cuda_error(e, "three_nn workspace free");
+    }
+    return DE6D_OK;
+}
 
 extern "C" int de6d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
                                int *idx, cudaStream_t stream) {

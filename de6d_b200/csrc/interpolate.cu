@@ -154,16 +154,30 @@ three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ gra
 
 using namespace de6d;
 
-extern "C" int de6d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
-                             cudaStream_t stream) {
+int de6d_three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *workspace,
+                       size_t workspace_bytes, cudaStream_t s);   // ball_query.cu
+
+extern "C" size_t de6d_ball_query_workspace_bytes(int b, int n);
+
+// impl: 0 automatic (grid search for >= 2048 known points), 1 brute-force scan, 2 grid.  workspace: as for ball query
+// over `known` (de6d_ball_query_workspace_bytes(b, m)), or NULL (stream-ordered scratch).
+extern "C" int de6d_three_nn_ex(int impl, int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                                void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (b < 0 || n < 0 || m < 0) return de6d_set_error(DE6D_ERR_INVALID, "three_nn: negative size");
     if (b == 0 || n == 0) return DE6D_OK;
     if (!unknown || !dist2 || !idx || (m > 0 && !known)) return de6d_set_error(DE6D_ERR_INVALID, "three_nn: null pointer");
     if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "three_nn: batch > 65535");
+    if (m >= 3 && (impl == 2 || (impl == 0 && m >= 2048)))
+        return de6d_three_nn_grid(b, n, m, unknown, known, dist2, idx, workspace, workspace_bytes, stream);
     dim3 grid(ceil_div(n, NN_THREADS), b);
     three_nn_kernel<<<grid, NN_THREADS, 0, stream>>>(n, m, unknown, known, dist2, idx);
     DE6D_CHECK_LAUNCH("three_nn_kernel");
     return DE6D_OK;
+}
+
+extern "C" int de6d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                             cudaStream_t stream) {
+    return de6d_three_nn_ex(0, b, n, m, unknown, known, dist2, idx, nullptr, 0, stream);
 }
 
 extern "C" int de6d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,

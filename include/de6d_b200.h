@@ -141,6 +141,10 @@ int de6d_group_points_grad(int b, int c, int n, int npoints, int nsample, const 
  * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) SQUARED distances, idx (b,n,3). */
 int de6d_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
                   cudaStream_t stream);
+/* Explicit form: impl 0 = automatic (grid search over `known` for m >= 2048, identical results), 1 = brute-force scan,
+ * 2 = grid; workspace = de6d_ball_query_workspace_bytes(b, m) bytes of device scratch, or NULL (cudaMallocAsync). */
+int de6d_three_nn_ex(int impl, int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx,
+                     void *workspace, size_t workspace_bytes, cudaStream_t stream);
 /* three_interpolate_wrapper(b, c, m, n, points, idx, weight, out)   interpolate.cpp:33-45, interpolate_gpu.cu:84-124 */
 int de6d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight,
                            float *out, cudaStream_t stream);

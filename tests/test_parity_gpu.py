@@ -474,6 +474,32 @@ def test_three_nn_interpolate_vs_oracle(orc, ops):
     np.testing.assert_array_equal(i2.cpu().numpy(), wi2); np.testing.assert_array_equal(d2.cpu().numpy(), wd2)
 
 
+@pytest.mark.parametrize("kind", ["uniform", "lidar", "dup", "lattice", "far"])
+@pytest.mark.parametrize("impl", [0, 1, 2])
+def test_three_nn_grid_vs_oracle(orc, kind, impl):
+    """three_nn: brute-force scan, grid search (3x3x3 then 5x5x5 cells of ~2 known points, full scan when the third
+    neighbour cannot be proven final) and the automatic choice against the oracle -- distances and indices, with
+    duplicated known points and lattices (exact ties: smallest index wins), queries far outside the known cloud."""
+    from de6d_b200.compat import pointnet2_batch_cuda as p2
+    rng = np.random.default_rng(5)
+    B, n, m = 2, 5000, 4096
+    if kind == "lidar":
+        known = synth.lidar_clouds(B, m, seed=1); unknown = synth.lidar_clouds(B, 8192, seed=2)[:, :n]
+    elif kind == "lattice":
+        g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+        known = np.stack([g[rng.permutation(m)], g[rng.permutation(m)]]); unknown = (rng.integers(0, 16, (B, n, 3)) + 0.5).astype(np.float32)
+    else:
+        known = synth.clouds(B, m, seed=1, dup_frac=0.3 if kind == "dup" else 0.0); unknown = synth.clouds(B, n, seed=2)
+        if kind == "far":
+            unknown[:, :500] += 300.0
+    unknown = np.ascontiguousarray(unknown)
+    d2 = torch.zeros((B, n, 3), device="cuda"); idx = torch.zeros((B, n, 3), dtype=torch.int32, device="cuda")
+    p2.three_nn_wrapper(B, n, m, cu(unknown), cu(known), d2, idx, impl=impl)
+    wd, wi = orc.three_nn(unknown, known)
+    np.testing.assert_array_equal(idx.cpu().numpy(), wi)
+    np.testing.assert_array_equal(np.sqrt(d2.cpu().numpy()), wd)
+
+
 @pytest.mark.parametrize("B,C,m,n", [(2, 19, 1100, 3000), (2, 5, 1101, 3001), (1, 64, 4096, 16384), (3, 3, 52, 200), (1, 70, 20000, 24000)])
 def test_three_interpolate_staged_and_direct_vs_oracle(orc, ops, B, C, m, n):
     """three_interpolate: the TMA-staged kernel (aligned shapes, rows in shared memory) and the direct kernel
