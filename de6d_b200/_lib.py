@@ -106,9 +106,20 @@ def trace_end():
     return out
 
 
+_fn_cache = {}
+
+
 def call(name, *args):
     """Invoke a status-returning entry point; raise De6dError with the library's message on failure."""
-    lib = load()
+    lib = _lib or load()
+    if _trace is None:
+        fn = _fn_cache.get(name)
+        if fn is None:
+            fn = _fn_cache[name] = getattr(lib, name)
+        rc = fn(*args)
+        if rc != 0:
+            raise De6dError("%s failed (code %d): %s" % (name, rc, lib.de6d_last_error_string().decode()))
+        return
     if _trace is not None:
         import torch
         s = torch.cuda.current_stream()

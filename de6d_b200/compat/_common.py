@@ -1,10 +1,17 @@
-"""Tensor checks and pointer plumbing shared by the compat modules."""
+"""Tensor checks and pointer plumbing shared by the compat modules.  Kept lean: in eager mode the reference calls these
+ops thousands of times per second and a wrapper that costs more host time than the kernel takes on the device would
+cap the speed-up (the raw-stream / device queries below are the C-level calls behind torch.cuda.current_stream())."""
 import torch
 
 from .._lib import call  # noqa: F401  (re-exported)
 
+_get_device = torch._C._cuda_getDevice if hasattr(torch._C, "_cuda_getDevice") else torch.cuda.current_device
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
 
 def stream_ptr():
+    if _raw_stream is not None:
+        return _raw_stream(_get_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -19,8 +26,8 @@ def dev(t, name, dtype):
         raise ValueError("%s must be contiguous" % name)
     if t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
-    if t.device.index != torch.cuda.current_device():
-        raise ValueError("%s is on cuda:%d but the current device is cuda:%d" % (name, t.device.index, torch.cuda.current_device()))
+    if t.get_device() != _get_device():
+        raise ValueError("%s is on cuda:%d but the current device is cuda:%d" % (name, t.get_device(), _get_device()))
     return t.data_ptr()
 
 
