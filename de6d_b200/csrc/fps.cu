@@ -133,6 +133,9 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     static_assert(BPW <= 32, "one owner lane per bucket");
     static_assert(!CL || MODE == FPS_D, "the cluster variant covers D-FPS");
     static_assert(SPECK == 1 || (MODE == FPS_D && !CL && PRUNE && 2 * NW <= 32), "multi-sample rounds: single-CTA pruned D-FPS");
+    // tie priorities in shared memory instead of registers: the multi-sample variant, and S-FPS with 32 slots per lane
+    // (min-distances + weights + packed priorities would not fit 128 registers)
+    constexpr bool SCP = SPECK > 1 || (MODE == FPS_S && BPW == 32 && !CL);
     if (m <= 0) return;
     int rank = 0, S = 1, cloud = blockIdx.x;
     if (CL) {
@@ -280,7 +283,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         }
         sx[p] = x; sy[p] = y; sz[p] = z;
         temp[j] = t0;
-        if (SPECK > 1) scp[p] = (unsigned short)cp;
+        if (SCP) scp[p] = (unsigned short)cp;
         else cpk[j >> 1] |= cp << (16 * (j & 1));
         if (PRUNE) {
             const bool valid = k != 0xffffffffu;
@@ -324,7 +327,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
             if (p < n) {
                 float val = wt[j];
                 uint32_t vv = (val == val) ? f2ord(val) : 0u;
-                uint32_t ww = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+                const uint32_t cpf = SCP ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                uint32_t ww = (cpf << 14) | (uint32_t)p;
                 if (vv > v || (vv == v && ww < wd)) { v = vv; wd = ww; }
             }
         }
@@ -350,7 +354,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         float t = temp[j];
         float val = MODE == FPS_S ? sfps_key(t, wt[j]) : t;
         uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
-        const uint32_t cp0 = SPECK > 1 ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        const uint32_t cp0 = SCP ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
         uint32_t wd = (cp0 << 14) | (uint32_t)p;
         uint32_t tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
         const uint32_t v_own = v, wd_own = wd;
@@ -530,7 +534,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                     temp[j] = t;
                     float val = MODE == FPS_S ? sfps_key(t, wt[MODE == FPS_S ? j : 0]) : t;
                     uint32_t v = (p < n && val == val) ? f2ord(val) : 0u;
-                    uint32_t wd = (((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu) << 14) | (uint32_t)p;
+                    const uint32_t cpv = SCP ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                    uint32_t wd = (cpv << 14) | (uint32_t)p;
                     uint32_t tm;
                     if (MODE == FPS_S) tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
                     warp_argmax(v, wd);
@@ -614,7 +619,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
     for (int j = 0; j < BPW; ++j) {
         const int p = ((j * NW + w) << 5) | lane;
         if (p < n) {
-            uint32_t cp = SPECK > 1 ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+            uint32_t cp = SCP ? (uint32_t)scp[p] : ((cpk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
             temp_g[index_of_cprio(cp, log2B, ibits)] = temp[j];
         }
     }
@@ -767,7 +772,7 @@ static int launch_bucket(int b, int n, int m, int log2B, int ibits, const float 
                          int *idx, cudaStream_t s) {
     constexpr int CAP = NW * BPW * 32;
     size_t smem = (size_t)CAP * 12 + 2 * NW * sizeof(uint2) + 6 * NW * sizeof(float) + 16 + 2 * 8 * 8 * 4 + 16 +
-                  2 * NW * 16 + 2 * NW * 4 + (SPECK > 1 ? (size_t)CAP * 2 : 0) + 16;
+                  2 * NW * 16 + 2 * NW * 4 + ((SPECK > 1 || (MODE == FPS_S && BPW == 32)) ? (size_t)CAP * 2 : 0) + 16;
     static unsigned long long devs = 0;
     if (int rc = de6d_ensure_smem(fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK>, (int)smem, devs, "fps smem attribute")) return rc;
     fps_bucket_kernel<MODE, NW, BPW, PRUNE, false, SPECK><<<b, NW * 32, smem, s>>>(n, m, log2B, ibits, xyz, w, temp, idx);
