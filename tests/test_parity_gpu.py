@@ -737,6 +737,30 @@ def test_against_live_reference_kernels(ref_modules, ops, lib):
     assert torch.equal(ru.points_in_boxes_gpu(pts, bxs), ref_o)
 
 
+def test_degenerate_sizes_do_not_launch_or_crash(ops):
+    """Empty batches / clouds / query sets / channel counts through the Python mirror: shapes come back right, nothing
+    faults (the reference would launch zero-sized grids and exit(-1) on the launch error)."""
+    pu, iu, ru = ops
+    z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device="cuda")  # noqa: E731
+    assert pu.furthest_point_sample(z(0, 10, 3), 4).shape == (0, 4)
+    assert pu.furthest_point_sample(z(2, 10, 3), 0).shape == (2, 0)
+    assert pu.ball_query(0.5, 4, z(2, 10, 3), z(2, 0, 3)).shape == (2, 0, 4)
+    cnt, idx = pu.ball_query_cnt(0.5, 4, z(2, 0, 3), z(2, 5, 3))
+    assert cnt.shape == (2, 5) and int(cnt.sum()) == 0 and int(idx.sum()) == 0
+    assert pu.grouping_operation(z(2, 0, 7), z(2, 3, 4, dt=torch.int32)).shape == (2, 0, 3, 4)
+    assert pu.gather_operation(z(2, 3, 7), z(2, 0, dt=torch.int32)).shape == (2, 3, 0)
+    assert pu.group_concat(z(1, 8, 3), z(1, 2, 3), None, z(1, 2, 4, dt=torch.int32)).shape == (1, 3, 2, 4)
+    d, i = pu.three_nn(z(1, 4, 3), z(1, 2, 3))
+    assert bool(torch.isinf(d[..., 2]).all()) and int(i[..., 2].sum()) == 0     # two known points: third slot stays (inf, 0)
+    assert iu.boxes_iou_bev(z(0, 7), z(5, 7)).shape == (0, 5)
+    keep, _ = iu.nms_gpu(z(0, 7), z(0), 0.1)
+    assert keep.numel() == 0
+    assert ru.points_in_boxes_gpu(z(1, 0, 3), z(1, 4, 7)).shape == (1, 0)
+    assert int((ru.points_in_boxes_gpu(z(1, 6, 3), z(1, 0, 7)) + 1).sum()) == 0
+    assert pu.calc_dist_matrix_for_sampling(z(1, 1, 3), None, 1.0).shape == (1, 1, 1)
+    torch.cuda.synchronize()
+
+
 # ------------------------------------------------------------------------------------------------ the chain
 def test_chain_graph_equals_eager_and_shards_concatenate(lib):
     from de6d_b200 import chain
