@@ -9,6 +9,7 @@ or PyTorch fallback.  Layout:
     roiaware_pool3d_utils.py
     model_nms_utils.py        class_agnostic_nms and its batched, host-sync-free form (post-processing)
     box_utils.py              full-pose (9-DoF) points_in_boxes3d on the device
+    staging.py                sample_points selection + break_up_pc: raw frames -> (B,N,3) / (B,C,N) in one kernel
     chain.py                  the SA + NMS op chain of BASELINE.json (streams + CUDA graph)
     dist.py                   frame sharding across ranks, NCCL gather of detections
     synth.py                  seeded synthetic KITTI-shape inputs

@@ -196,6 +196,18 @@ int de6d_points_in_boxes_mask(int t, int m, const float *boxes, const float *pts
  * LAST box containing the point (later boxes overwrite earlier ones, like the reference loop), -1 if none. */
 int de6d_points_in_boxes9(int b, int t, int m, const float *boxes, const float *pts, long long *out, cudaStream_t stream);
 
+/* ---- next to the path: input staging ----------------------------------------------------- */
+
+/* DataProcessor.sample_points gather (datasets/processor/data_processor.py:145-177: points[choice]) + break_up_pc and
+ * the per-frame count / view / permute copies of PointNet2FSMSG.forward (backbones_3d/pointnet2_backbone.py:193-222) in
+ * one pass: src (total_rows, lead+3+c) f32 rows [batch_idx (lead=1 only), x, y, z, c features]; choice NULL (row bs*n+i,
+ * requires total_rows == b*n) or (b,n) i32 global row indices -> xyz (b,n,3), features (b,c,n) (NULL allowed when c == 0),
+ * batch_idx (b,n) f32 or NULL, status i32[2] or NULL (zeroed by the call): [0] = rows whose batch column differs from the
+ * frame slot they were written to (the equal-count assertion of pointnet2_backbone.py:214-218 holds iff it is 0),
+ * [1] = choice entries outside [0,total_rows) (those points are written as zeros). */
+int de6d_stage_points(int b, int n, int c, int lead, long long total_rows, const float *src, const int *choice, float *xyz,
+                      float *features, float *batch_idx, int *status, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

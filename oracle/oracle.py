@@ -252,3 +252,18 @@ def points_in_boxes3d(points, boxes3d):
     out = np.full(pts.shape[0], -1, np.int64)
     lib().orc_points_in_boxes9(boxes.shape[0], pts.shape[0], _fp(boxes), _fp(pts), out.ctypes.data_as(C.POINTER(C.c_int64)))
     return out
+
+
+def break_up_pc(points, batch_size):
+    """pointnet2_backbone.py:193-222 restated with numpy: points (B*N, 4+C) rows [batch_idx, x, y, z, features...] ->
+    (batch_idx (B,N) f32, xyz (B,N,3), features (B,C,N) or None); asserts that every frame holds the same number of rows
+    like the reference (:214-218)."""
+    pc = _f32(points)
+    bidx = pc[:, 0]
+    cnt = np.array([(bidx == b).sum() for b in range(batch_size)])
+    assert cnt.min() == cnt.max()
+    xyz = np.ascontiguousarray(pc[:, 1:4]).reshape(batch_size, -1, 3)
+    feats = None
+    if pc.shape[1] > 4:
+        feats = np.ascontiguousarray(pc[:, 4:].reshape(batch_size, -1, pc.shape[1] - 4).transpose(0, 2, 1))
+    return bidx.reshape(batch_size, -1).astype(np.float32), xyz, feats
