@@ -217,6 +217,9 @@ nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ n
     __shared__ unsigned int s_last;
     __shared__ unsigned long long s_diag[64];
     __shared__ unsigned long long s_keepbits;
+    __shared__ unsigned long long s_words[64];
+    __shared__ unsigned short s_queue[64 * 64];
+    __shared__ int s_qn;
 
     const int f = blockIdx.y;
     const int cb = ceil_div(n, 64);
@@ -240,23 +243,55 @@ nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ n
         __syncthreads();
         const int r = tid >> 2, part = tid & 3;  // row r, columns part*16 .. +15
         const int gi = rt * 64 + r;
-        unsigned int bits = 0;
-        if (gi < nv) {
-            const int jstart = (rt == ct) ? r + 1 : 0;
-            for (int jj = 0; jj < 16; ++jj) {
-                const int j = part * 16 + jj, gj = ct * 64 + j;
-                if (j < jstart || gj >= nv) continue;
-                float v;
-                if (NORMAL) v = iou_axis_aligned(boxes + (size_t)gi * 7, boxes + (size_t)gj * 7);
-                else v = iou_from_overlap(overlap_area(grow[r], gcol[j]), grow[r].area, gcol[j].area);
-                if (v > thresh) bits |= 1u << jj;
+        if (NORMAL) {
+            unsigned int bits = 0;
+            if (gi < nv) {
+                const int jstart = (rt == ct) ? r + 1 : 0;
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int j = part * 16 + jj, gj = ct * 64 + j;
+                    if (j < jstart || gj >= nv) continue;
+                    if (iou_axis_aligned(boxes + (size_t)gi * 7, boxes + (size_t)gj * 7) > thresh) bits |= 1u << jj;
+                }
             }
+            // four adjacent lanes hold the four 16-bit quarters of the word
+            unsigned long long word = (unsigned long long)bits << (16 * part);
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            if (part == 0 && gi < n) mask[(size_t)gi * cb + ct] = word;
+        } else {
+            // Two phases, because only a few percent of the pairs survive the bounding-circle test and the polygon
+            // clipping behind it is ~2000 instructions: evaluated in place, one surviving pair stalls the other 31 lanes
+            // of its warp.  Phase 1 queues the surviving pairs of the tile, phase 2 hands them out densely.
+            if (tid < 64) s_words[tid] = 0ull;
+            if (tid == 0) s_qn = 0;
+            __syncthreads();
+            if (gi < nv) {
+                const int jstart = (rt == ct) ? r + 1 : 0;
+                unsigned int cand = 0;
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int j = part * 16 + jj, gj = ct * 64 + j;
+                    if (j < jstart || gj >= nv) continue;
+                    if (!cannot_touch(grow[r], gcol[j])) cand |= 1u << jj;
+                }
+                if (cand) {
+                    int at = atomicAdd(&s_qn, __popc(cand));
+                    while (cand) {
+                        const int jj = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        s_queue[at++] = (unsigned short)(r * 64 + part * 16 + jj);
+                    }
+                }
+            }
+            __syncthreads();
+            const int qn = s_qn;
+            for (int q = tid; q < qn; q += NMS_T) {
+                const int code = s_queue[q], qr = code >> 6, qj = code & 63;
+                const float v = iou_from_overlap(overlap_area(grow[qr], gcol[qj]), grow[qr].area, gcol[qj].area);
+                if (v > thresh) atomicOr(&s_words[qr], 1ull << qj);
+            }
+            __syncthreads();
+            if (tid < 64 && rt * 64 + tid < n) mask[(size_t)(rt * 64 + tid) * cb + ct] = s_words[tid];
         }
-        // four adjacent lanes hold the four 16-bit quarters of the word
-        unsigned long long word = (unsigned long long)bits << (16 * part);
-        word |= __shfl_xor_sync(0xffffffffu, word, 1);
-        word |= __shfl_xor_sync(0xffffffffu, word, 2);
-        if (part == 0 && gi < n) mask[(size_t)gi * cb + ct] = word;
     } else {
         const int r = tid >> 2, gi = rt * 64 + r;
         if ((tid & 3) == 0 && gi < n) mask[(size_t)gi * cb + ct] = 0ull;

@@ -237,6 +237,30 @@ def test_fused_ffps_adversarial_ties(ops, C, M, kind):
     assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M), two)
 
 
+@pytest.mark.parametrize("N,kind", [(4096, "dup"), (4096, "equal_features"), (3600, "plain"), (4224, "plain"), (4100, "dup")])
+def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
+    """The 6-CTA (704 points per CTA, uneven last slice) and 8-CTA cluster forms of the fused F-FPS kernel pick the same
+    indices as the two-call path, ties included (the launcher chooses between them by batch size; forced here)."""
+    pu = ops[0]
+    B, C, M = 3, 64, 1024 if kind == "dup" else 300
+    rng = np.random.default_rng(N)
+    xyz = synth.clouds(B, N, seed=11, dup_frac=0.3 if kind == "dup" else 0.0)
+    feats = synth.features(B, C, N, seed=11)
+    if kind == "dup":
+        src = rng.integers(0, N, N // 2); dst = rng.permutation(N)[: N // 2]
+        feats[:, :, dst] = feats[:, :, src]; xyz[:, dst] = xyz[:, src]
+    elif kind == "equal_features":
+        feats[:] = 1.0
+    x, f = cu(xyz), cu(feats).permute(0, 2, 1)
+    two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
+    for s in ("6", "8"):
+        monkeypatch.setenv("DE6D_FF_CLUSTER", s)
+        assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M), two), "cluster size " + s
+    monkeypatch.delenv("DE6D_FF_CLUSTER")
+    big = pu.furthest_point_sample_features(x.repeat(6, 1, 1), f.repeat(6, 1, 1), 1.0, M)   # 18 clouds: the launcher's own pick
+    assert torch.equal(big[:3], two) and torch.equal(big[15:], two)
+
+
 def test_fused_ffps_full_batch(ops):
     """Layer-2 shape of the chain at batch 16 (more clusters than fit at once: several waves)."""
     pu = ops[0]
