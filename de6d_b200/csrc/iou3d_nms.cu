@@ -161,6 +161,8 @@ iou_matrix_kernel(int na, const float *__restrict__ boxes_a, int nb, const float
                   float *__restrict__ out) {
     __shared__ BoxGeo ga[MT], gb[MT];
     __shared__ float za[MT][3], zb[MT][3];  // zmax, zmin, volume (MODE 2)
+    __shared__ unsigned short s_queue[MT * MT];
+    __shared__ int s_qn;
     const int a0 = blockIdx.y * MT, b0 = blockIdx.x * MT;
     const int tid = threadIdx.x;
     if (tid < 2 * MT) {
@@ -179,24 +181,35 @@ iou_matrix_kernel(int na, const float *__restrict__ boxes_a, int nb, const float
         }
     }
     __syncthreads();
+    // value of one matrix entry from the BEV overlap s
+    auto entry = [&](float s, int i, int j) -> float {
+        if (MODE == 0) return s;
+        if (MODE == 1) return iou_from_overlap(s, ga[i].area, gb[j].area);
+        float h = __fsub_rn(fminf(za[i][0], zb[j][0]), fmaxf(za[i][1], zb[j][1]));
+        h = fmaxf(h, 0.f);  // torch.clamp(min=0): NaN propagates in torch, fmaxf drops it; inputs are finite boxes
+        const float o3 = __fmul_rn(s, h);
+        const float den = fmaxf(__fsub_rn(__fadd_rn(za[i][2], zb[j][2]), o3), 1e-6f);
+        return __fdiv_rn(o3, den);
+    };
+    // Phase 1: pairs whose bounding circles are apart have overlap 0 and are written at once; the others are queued
+    // and clipped densely in phase 2 (a warp would otherwise wait on every lane that needs the ~2000-instruction clip).
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
     const int j = tid & 31, bj = b0 + j;
-    if (bj >= nb) return;
+    if (bj < nb) {
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
-        const int i = (tid >> 5) + 8 * r, ai = a0 + i;
-        if (ai >= na) break;
-        const float s = overlap_area(ga[i], gb[j]);
-        float v;
-        if (MODE == 0) v = s;
-        else if (MODE == 1) v = iou_from_overlap(s, ga[i].area, gb[j].area);
-        else {
-            float h = __fsub_rn(fminf(za[i][0], zb[j][0]), fmaxf(za[i][1], zb[j][1]));
-            h = fmaxf(h, 0.f);  // torch.clamp(min=0): NaN propagates in torch, fmaxf drops it; inputs are finite boxes
-            const float o3 = __fmul_rn(s, h);
-            const float den = fmaxf(__fsub_rn(__fadd_rn(za[i][2], zb[j][2]), o3), 1e-6f);
-            v = __fdiv_rn(o3, den);
+        for (int r = 0; r < 4; ++r) {
+            const int i = (tid >> 5) + 8 * r, ai = a0 + i;
+            if (ai >= na) break;
+            if (cannot_touch(ga[i], gb[j])) out[(size_t)ai * nb + bj] = entry(0.f, i, j);
+            else s_queue[atomicAdd(&s_qn, 1)] = (unsigned short)(i * MT + j);
         }
-        out[(size_t)ai * nb + bj] = v;
+    }
+    __syncthreads();
+    const int qn = s_qn;
+    for (int q = tid; q < qn; q += 256) {
+        const int code = s_queue[q], i = code / MT, jq = code % MT;
+        out[(size_t)(a0 + i) * nb + b0 + jq] = entry(overlap_area(ga[i], gb[jq]), i, jq);
     }
 }
 
