@@ -807,6 +807,10 @@ static int launch_bucket_cluster(int b, int n, int m, const float *xyz, float *t
     return DE6D_OK;
 }
 
+// fps_small.cu: register-resident kernel for clouds of 32..4096 points; -1 = shape not covered
+int fps_small_dispatch(int mode, int b, int n, int m, int log2B, const float *xyz, const float *w, float *temp, int *idx,
+                       cudaStream_t s);
+
 template <int MODE>
 static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, float *temp, int *idx, int impl,
                         cudaStream_t s) {
@@ -818,6 +822,10 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, f
     int ibits = 0;
     while (((n - 1) >> log2B) >> ibits) ++ibits;
     const bool prune = impl != 1;
+    if (impl == 0 || impl == 6) {   // small clouds: every point every sample out of registers beats the bucket machinery
+        const int rc = fps_small_dispatch(MODE == FPS_S ? 1 : 0, b, n, m, log2B, xyz, w, temp, idx, s);
+        if (rc != -1) return rc;
+    }
     if (n <= 16384 && impl == 3 && log2B + ibits <= 14) {   // experimental: twice the warps, half the buckets per warp
         if (n <= 1024) return launch_bucket<MODE, 16, 2, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
         if (n <= 4096) return launch_bucket<MODE, 32, 4, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);

@@ -78,7 +78,8 @@ int de6d_furthest_point_sampling_weights(int b, int n, int m, const float *xyz, 
 
 /* Same results, explicit kernel choice (testing / benchmarking): impl 0 = default, 1 = on-chip kernel with bucket
  * pruning disabled, 2 = generic global-memory kernel, 3 = twice the warps, 4 = pruned, one sample per barrier round,
- * 5 = pruned, up to four samples per round (exact speculation; the default above 4096 points). */
+ * 5 = pruned, up to four samples per round (exact speculation; the default above 4096 points), 6 = register-resident
+ * kernel without pruning for clouds of 32..4096 points (the default there; other sizes fall through to the default). */
 int de6d_furthest_point_sampling_impl(int b, int n, int m, const float *xyz, float *temp, int *idx, int impl,
                                       cudaStream_t stream);
 int de6d_furthest_point_sampling_weights_impl(int b, int n, int m, const float *xyz, const float *weights,

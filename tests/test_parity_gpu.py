@@ -130,6 +130,27 @@ def test_dfps_multi_sample_rounds_exact(orc, lib, N, M, kind):
         np.testing.assert_array_equal(temp, wtemp)
 
 
+@pytest.mark.parametrize("B,N,M", [(7, 512, 256), (5, 64, 64), (6, 100, 37), (9, 1024, 200), (3, 1500, 300), (2, 3072, 500),
+                                   (5, 32, 32), (4, 1023, 1023), (3, 4095, 100), (13, 640, 50)])
+def test_small_cloud_register_kernel(orc, lib, B, N, M):
+    """Clouds of 32..4096 points take the register-resident kernel (fps_small.cu; several one-warp clouds per CTA, partial
+    last CTA, every (B = opt_n_threads, C = ceil(N/B)) layout): D-FPS and S-FPS == oracle == bucket kernel, indices and
+    min-distances, with duplicated points so that the tie order matters."""
+    xyz = synth.clouds(B, N, seed=3 * N + B, dup_frac=0.3)
+    want, wtemp = orc.furthest_point_sample(xyz, M, return_temp=True)
+    for impl in (0, 6, 4):
+        idx, temp = _fps_impl(xyz, M, impl)
+        np.testing.assert_array_equal(idx, want)
+        np.testing.assert_array_equal(temp, wtemp)
+    w = synth.weights(B, N, seed=N)
+    w[:, :3] = 0.0; w[:, 3:6] = 1e-13; w[:, 6:12] = w[:, 12:18]        # double path + tied weights
+    want, wtemp = orc.furthest_point_sample_weights(xyz, w, M, return_temp=True)
+    for impl in (0, 6, 4):
+        idx, temp = _fps_impl(xyz, M, impl, weights=w)
+        np.testing.assert_array_equal(idx, want)
+        np.testing.assert_array_equal(temp, wtemp)
+
+
 def test_dfps_all_points_identical_and_caller_temp(orc, lib, ops):
     # every distance ties at 0: the tie rule alone decides
     xyz = np.ones((1, 777, 3), np.float32)
