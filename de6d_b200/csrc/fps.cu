@@ -416,9 +416,14 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                     temp[j] = t;
                     const uint32_t v_own = (p < n && t == t) ? f2ord(t) : 0u;
                     const uint32_t wd_own = ((uint32_t)cps << 14) | (uint32_t)p;
-                    uint32_t v = v_own, wd = wd_own;
-                    warp_argmax(v, wd);
-                    const uint32_t sec = __reduce_max_sync(0xffffffffu, wd_own == wd ? 0u : v_own);
+                    // bucket maximum, its owner (smallest word among the lanes at the maximum) and the second-best value.
+                    // The second-best is the maximum again when two lanes tie, else the best value below it: both
+                    // REDUX after the first depend on the maximum only, so they overlap instead of forming a chain.
+                    const uint32_t v = __reduce_max_sync(0xffffffffu, v_own);
+                    const bool top = v_own == v;
+                    const uint32_t wd = __reduce_min_sync(0xffffffffu, top ? wd_own : 0xffffffffu);
+                    const uint32_t below = __reduce_max_sync(0xffffffffu, top ? 0u : v_own);
+                    const uint32_t sec = __popc(__ballot_sync(0xffffffffu, top)) > 1 ? v : below;
                     if (lane == j) { bval = v; bword = wd; bmaxt = v ? ord2f(v) : -INFINITY; bval2 = sec; }
                 }
             };

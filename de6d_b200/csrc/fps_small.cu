@@ -180,13 +180,15 @@ int fps_small_dispatch(int mode, int b, int n, int m, int log2B, const float *xy
     const int B = 1 << log2B;
     const int C = (n + B - 1) / B;
     const int need = (B / 32) * C;      // slots per lane over the whole cloud
+    // S-FPS keeps five values per point: 32 points per lane would spill (measured slower than the bucket kernel), so
+    // it stops at 16 per lane (2048 points); D-FPS goes to 32 per lane.
 #define DE6D_FS(W_, R_)                                                                                   \
     return mode == 0 ? fs_launch<0, W_, R_>(b, n, m, log2B, C, xyz, w, temp, idx, s)                      \
                      : fs_launch<1, W_, R_>(b, n, m, log2B, C, xyz, w, temp, idx, s)
     if (need <= 16) { DE6D_FS(1, 16); }
-    if (need <= 32) { DE6D_FS(1, 32); }
+    if (need <= 32 && mode == 0) return fs_launch<0, 1, 32>(b, n, m, log2B, C, xyz, w, temp, idx, s);
     if (need <= 64) { DE6D_FS(4, 16); }
-    if (need <= 128) { DE6D_FS(4, 32); }
+    if (need <= 128 && mode == 0) return fs_launch<0, 4, 32>(b, n, m, log2B, C, xyz, w, temp, idx, s);
 #undef DE6D_FS
     return -1;
 }
