@@ -37,13 +37,11 @@ fps_small_kernel(int b, int n, int m, int log2B, int C, int cinv, const float *_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ww = warp % W;                        // warp index inside its cloud
     const int cloud = blockIdx.x * CPB + warp / W;
-    const bool live = cloud < b;
-    if (!live) return;   // W == 4: whole CTAs; W == 1: whole warps, and a one-warp cloud uses no CTA barrier below
-    const int cl = cloud;
-    const float *xyz = xyz_all + (size_t)cl * n * 3;
-    const float *wts = MODE == 1 ? w_all + (size_t)cl * n : nullptr;
-    float *temp_g = temp_all + (size_t)cl * n;
-    int *idxs = idx_all + (size_t)cl * m;
+    if (cloud >= b) return;   // W == 4: whole CTAs; W == 1: whole warps, and a one-warp cloud uses no CTA barrier below
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    const float *wts = MODE == 1 ? w_all + (size_t)cloud * n : nullptr;
+    float *temp_g = temp_all + (size_t)cloud * n;
+    int *idxs = idx_all + (size_t)cloud * m;
     float *sxyz = fs_smem + (size_t)(warp / W) * n * 3;   // this cloud's coordinates, AoS like the input
 
     const int hbits = log2B - 5;
@@ -51,17 +49,15 @@ fps_small_kernel(int b, int n, int m, int log2B, int C, int cinv, const float *_
     const uint32_t lanepart = (__brev((uint32_t)lane) >> 27) << (hbits + 22);
 
     // ---- load: coordinates -> smem copy + registers in tie order --------------------------------------------------
-    if (live) {
-        if (W == 1) for (int e = lane; e < 3 * n; e += 32) sxyz[e] = xyz[e];
-        else for (int e = tid; e < 3 * n; e += FS_THREADS) sxyz[e] = xyz[e];
-    }
+    if (W == 1) for (int e = lane; e < 3 * n; e += 32) sxyz[e] = xyz[e];
+    else for (int e = tid; e < 3 * n; e += FS_THREADS) sxyz[e] = xyz[e];
     float x[RPL], y[RPL], z[RPL], t[RPL], wt[MODE == 1 ? RPL : 1];
 #pragma unroll
     for (int jj = 0; jj < RPL; ++jj) {
         const uint32_t J = (uint32_t)(ww * RPL + jj);
         const uint32_t a = J / (uint32_t)C, c = J - a * (uint32_t)C;
         const uint32_t k = c * B + ((hbits ? (__brev(a) >> (32 - hbits)) : 0u) << 5) + (uint32_t)lane;
-        const bool valid = live && a < (B >> 5) && k < (uint32_t)n;
+        const bool valid = a < (B >> 5) && k < (uint32_t)n;
         x[jj] = valid ? xyz[k * 3 + 0] : 0.f;
         y[jj] = valid ? xyz[k * 3 + 1] : 0.f;
         z[jj] = valid ? xyz[k * 3 + 2] : 0.f;
@@ -102,7 +98,7 @@ fps_small_kernel(int b, int n, int m, int log2B, int C, int cinv, const float *_
             const uint32_t J = (uint32_t)(ww * RPL + jj);
             const uint32_t a = J / (uint32_t)C, c = J - a * (uint32_t)C;
             const uint32_t k = c * B + ((hbits ? (__brev(a) >> (32 - hbits)) : 0u) << 5) + (uint32_t)lane;
-            const bool valid = live && a < (B >> 5) && k < (uint32_t)n;
+            const bool valid = a < (B >> 5) && k < (uint32_t)n;
             const float key = valid ? wt[jj] : -INFINITY;
             if (key > bt) { bt = key; bj = jj; }
         }
@@ -156,7 +152,7 @@ fps_small_kernel(int b, int n, int m, int log2B, int C, int cinv, const float *_
         const uint32_t J = (uint32_t)(ww * RPL + jj);
         const uint32_t a = J / (uint32_t)C, c = J - a * (uint32_t)C;
         const uint32_t k = c * B + ((hbits ? (__brev(a) >> (32 - hbits)) : 0u) << 5) + (uint32_t)lane;
-        if (live && a < (B >> 5) && k < (uint32_t)n) temp_g[k] = t[jj];
+        if (a < (B >> 5) && k < (uint32_t)n) temp_g[k] = t[jj];
     }
 }
 
