@@ -25,11 +25,11 @@ def test_python_prototypes_cover_header():
     assert sorted(_lib.PROTOTYPES) == _declared_symbols()
 
 
-def test_library_is_sm100a_and_torch_free():
+def test_library_is_sm100a_and_torch_free(lib):
     import subprocess
     from de6d_b200 import _lib
-    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
-    assert "sm_100a" in out
+    r = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert "sm_100a" in r.stdout, r.stdout[-500:]
     ldd = subprocess.run(["ldd", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     assert "torch" not in ldd and "c10" not in ldd
 
