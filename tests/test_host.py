@@ -117,3 +117,38 @@ def test_mirror_modules_expose_reference_names(lib):
         assert hasattr(iu, name), name
     for name in ("points_in_boxes_cpu", "points_in_boxes_gpu"):
         assert hasattr(ru, name), name
+
+
+def test_small_cloud_fps_register_layout_is_the_reference_tie_order():
+    """fps_small.cu keeps point k = c*B + (bitrev(a) << 5) + lane in slot J = a*C + c of its lane and relies on two facts:
+    every point of the cloud appears in exactly one (lane, slot), and within a lane the reference's tie priority
+    (common.cuh: fps_prio = bit-reversed (k mod B), then k / B) ascends with the slot -- so a strict '>' scan in slot
+    order picks the same point the reference's strided in-thread scan + tree reduction picks.  Checked here for every
+    layout class the launcher can choose (restating the index arithmetic of the kernel)."""
+    import math
+
+    def brev(x, bits):
+        return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+
+    for n in (32, 33, 40, 63, 64, 100, 300, 511, 512, 640, 777, 1000, 1023, 1024, 1025, 1500, 2048, 3000, 3072, 4095, 4096):
+        log2b = min(int(math.log(n) / math.log(2.0)), 10)
+        B, hbits = 1 << log2b, log2b - 5
+        C = (n + B - 1) // B
+        need = (B // 32) * C
+        assert need <= 128 and C <= 4
+        cinv = (65536 + C - 1) // C
+        seen = set()
+        for lane in range(32):
+            last = -1
+            for J in range(need):
+                a, c = J // C, J % C
+                assert (J * cinv) >> 16 == a                     # the multiply-shift division used in the sample loop
+                k = c * B + (brev(a, hbits) << 5) + lane
+                if k >= n:
+                    continue
+                seen.add(k)
+                prio = (brev(k % B, log2b) << 22) | (k // B)      # fps_prio
+                assert prio == ((brev(lane, 5) << hbits | a) << 22) | c
+                assert prio > last
+                last = prio
+        assert seen == set(range(n))
