@@ -75,7 +75,7 @@ def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, ga
     """F-FPS without the (B, N, N) matrix: identical indices to
         furthest_point_sample_matrix(calc_dist_matrix_for_sampling(xyz, features, gamma), npoint)
     (the reference's call pair, pointnet2_modules.py:383-388).  xyz (B, N, 3), features (B, N, C) with any strides.
-    One 8-CTA cluster per cloud evaluates only the selected rows out of distributed shared memory; shapes that do not
+    One thread-block cluster (6 or 8 CTAs) per cloud evaluates only the selected rows out of distributed shared memory; shapes that do not
     fit on chip take the two-call form."""
     from ._lib import call, load
     assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()

@@ -63,7 +63,7 @@ int de6d_dist_matrix(int b, int n, int c, const float *xyz, const float *feature
                      long long stride_n, long long stride_c, float gamma, float *out, cudaStream_t stream);
 
 /* Fused F-FPS: the indices de6d_dist_matrix + de6d_furthest_point_sampling_matrix would give (bit for bit), without the
- * (b,n,n) matrix: one 8-CTA thread-block cluster per cloud keeps the features in distributed shared memory and
+ * (b,n,n) matrix: one thread-block cluster (6 or 8 CTAs) per cloud keeps the features in distributed shared memory and
  * evaluates only the m selected rows (pointnet2_modules.py:383-388 is the call pair this replaces).  features as in
  * de6d_dist_matrix (element strides).  ..._fits(n, c) == 0: shape does not fit on chip, use the two-call form. */
 int de6d_furthest_point_sampling_features_fits(int n, int c);
