@@ -48,6 +48,8 @@ PROTOTYPES = {
     "de6d_points_in_boxes": [_i, _i, _i, _p, _p, _p, _p],
     "de6d_points_in_boxes9": [_i, _i, _i, _p, _p, _p, _p],
     "de6d_points_in_boxes_mask": [_i, _i, _p, _p, _p, _p],
+    "de6d_points_in_boxes_mask_host": [_i, _i, _p, _p, _p, _i],
+    "de6d_boxes_iou_bev_host": [_i, _p, _i, _p, _p, _i],
     "de6d_stage_points": [_i, _i, _i, _i, C.c_longlong, _p, _p, _p, _p, _p, _p, _p],
     "de6d_last_error_string": [],
     "de6d_version": [],

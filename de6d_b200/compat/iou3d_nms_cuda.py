@@ -5,6 +5,7 @@ from .._lib import load
 from ._common import call, dev, stream_ptr
 
 f32 = torch.float32
+HOST_THREADS = 1   # the reference loops are single-threaded; raise for bulk host-side use outside DataLoader workers
 
 
 def _boxes(t, name):
@@ -33,17 +34,23 @@ def boxes_iou3d_gpu(boxes_a, boxes_b, ans_iou):
 
 
 def boxes_iou_bev_cpu(boxes_a, boxes_b, ans_iou):
-    """The reference evaluates this on the host (iou3d_cpu.cpp:232-252).  Here the same arithmetic runs on the
-    B200: host tensors are staged to the device, computed with de6d_boxes_iou_bev and copied back."""
+    """Host tensors in, host tensor out, evaluated on the calling host thread like the reference
+    (iou3d_cpu.cpp:232-252) -- its callers run in forked DataLoader workers (database_sampler.py:232-233) where no CUDA
+    context may be created.  de6d_boxes_iou_bev_host: the reference's host arithmetic, bit-identical results.
+    (Callers that hold device tensors use boxes_iou_bev_gpu.)"""
     if boxes_a.is_cuda or boxes_b.is_cuda or ans_iou.is_cuda:
         raise ValueError("boxes_iou_bev_cpu takes CPU tensors")
-    if not (boxes_a.is_contiguous() and boxes_b.is_contiguous()):
-        raise ValueError("boxes must be contiguous")
-    a = boxes_a.to(device="cuda", dtype=f32)
-    b = boxes_b.to(device="cuda", dtype=f32)
-    out = torch.zeros((a.size(0), b.size(0)), dtype=f32, device="cuda")
-    boxes_iou_bev_gpu(a, b, out)
-    ans_iou.copy_(out)
+    for t, name in ((boxes_a, "boxes_a"), (boxes_b, "boxes_b"), (ans_iou, "ans_iou")):
+        if t.dtype != f32:
+            raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+    if boxes_a.dim() != 2 or boxes_a.size(1) != 7 or boxes_b.dim() != 2 or boxes_b.size(1) != 7:
+        raise ValueError("boxes must have shape (N, 7)")
+    if ans_iou.numel() < boxes_a.size(0) * boxes_b.size(0):
+        raise ValueError("ans_iou is too small")
+    call("de6d_boxes_iou_bev_host", boxes_a.size(0), boxes_a.data_ptr(), boxes_b.size(0), boxes_b.data_ptr(),
+         ans_iou.data_ptr(), HOST_THREADS)
     return 1
 
 

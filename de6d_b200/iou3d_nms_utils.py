@@ -16,13 +16,14 @@ def _to_torch(x):
 
 
 def boxes_bev_iou_cpu(boxes_a, boxes_b):
-    """(reference :12-28) CPU tensors / numpy in, same kind out; computed on the device."""
+    """(reference :12-28) CPU tensors / numpy in, same kind out; evaluated on the calling host thread like the reference
+    (safe inside forked DataLoader workers), bit-identical to it.  `boxes_iou_bev` is the device form."""
     boxes_a, is_numpy = _to_torch(boxes_a)
     boxes_b, _ = _to_torch(boxes_b)
     assert not (boxes_a.is_cuda or boxes_b.is_cuda), 'Only support CPU tensors'
     assert boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7
     ans_iou = boxes_a.new_zeros(torch.Size((boxes_a.shape[0], boxes_b.shape[0])))
-    _ext.boxes_iou_bev_cpu(boxes_a.contiguous(), boxes_b.contiguous(), ans_iou)
+    _ext.boxes_iou_bev_cpu(boxes_a.float().contiguous(), boxes_b.float().contiguous(), ans_iou)
     return ans_iou.numpy() if is_numpy else ans_iou
 
 

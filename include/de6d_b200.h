@@ -163,6 +163,12 @@ int de6d_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *bo
 /* boxes_iou_bev_gpu(boxes_a, boxes_b, ans_iou)   iou3d_nms.cpp:70-88, iou3d_nms_kernel.cu:251-265
  * Also serves boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252): same arithmetic, run on the device. */
 int de6d_boxes_iou_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, cudaStream_t stream);
+
+/* boxes_iou_bev_cpu(boxes_a, boxes_b, ans_iou)   iou3d_cpu.cpp:232-252 -- HOST pointers, evaluated on the calling
+ * thread (rows split over `nthreads` std::threads when > 1) with the reference's host arithmetic (libm trig): the
+ * reference calls this from forked DataLoader workers (database_sampler.py:232-233) where no CUDA context can exist.
+ * Bit-identical to the reference function.  Never touches the device. */
+int de6d_boxes_iou_bev_host(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, int nthreads);
 /* Fused boxes_iou3d_gpu (python composition iou3d_nms_utils.py:48-81: BEV overlap x height overlap / union volume). */
 int de6d_boxes_iou3d(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, cudaStream_t stream);
 
@@ -188,6 +194,11 @@ int de6d_points_in_boxes(int b, int t, int m, const float *boxes, const float *p
  * boxes (t,7), pts (m,3) -> (t,m) i32 0/1 mask, MARGIN 1e-2, host (unfused) arithmetic. */
 int de6d_points_in_boxes_mask(int t, int m, const float *boxes, const float *pts, int *point_indices,
                               cudaStream_t stream);
+
+/* points_in_boxes_cpu(boxes, pts, pts_indices)   roiaware_pool3d.cpp:143-168 -- HOST pointers, calling thread
+ * (+ optional row threads), MARGIN 1e-2, (t,m) 0/1 mask; for the reference's DataLoader-worker callers
+ * (kitti_dataset.py:248, box_utils.py:104).  Bit-identical to the reference function.  Never touches the device. */
+int de6d_points_in_boxes_mask_host(int t, int m, const float *boxes, const float *pts, int *point_indices, int nthreads);
 
 /* ---- next to the path: full-pose boxes -------------------------------------------------- */
 

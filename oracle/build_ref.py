@@ -52,6 +52,41 @@ def _run(cmd):
     return r.stdout
 
 
+# The reference's own Python on top of the extension modules (what "drop-in" has to run unchanged): staged verbatim into
+# oracle/_ref/py/ (git-ignored like the .so files, travels to the GPU box) so tests/test_dropin_gpu.py can execute it
+# once over de6d_b200.compat and once over oracle/_ref/*.so.  No __init__.py is staged: oracle/ref_py.py builds the
+# package tree by hand so that pcdet/__init__.py (needs the generated version.py) never runs.
+PY_FILES = [
+    "pcdet/ops/pointnet2/pointnet2_batch/pointnet2_utils.py",
+    "pcdet/ops/pointnet2/pointnet2_batch/pointnet2_modules.py",
+    "pcdet/ops/pointnet2/pointnet2_stack/pointnet2_utils.py",     # imported by pointnet2_modules.py:7
+    "pcdet/ops/iou3d_nms/iou3d_nms_utils.py",
+    "pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py",
+    "pcdet/models/model_utils/model_nms_utils.py",
+    "pcdet/utils/common_utils.py",
+    "pcdet/utils/box_utils.py",
+]
+PY_OUT = os.path.join(OUT, "py")
+
+
+def stage_python(force=False):
+    """Copy the reference wrapper files, byte for byte, into oracle/_ref/py/ (only where /root/reference exists)."""
+    import shutil
+    core = os.path.join(REF, "core")
+    if not os.path.isdir(core):
+        return python_available()
+    for rel in PY_FILES:
+        dst = os.path.join(PY_OUT, rel)
+        if force or not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(os.path.join(core, rel)):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(os.path.join(core, rel), dst)
+    return True
+
+
+def python_available():
+    return all(os.path.exists(os.path.join(PY_OUT, rel)) for rel in PY_FILES)
+
+
 def available():
     return all(os.path.exists(os.path.join(OUT, m + ".so")) for m in MODULES)
 
@@ -59,6 +94,7 @@ def available():
 def build(force=False, jobs=None):
     if not os.path.isdir(OPS):
         return False  # GPU box: only the prebuilt modules exist
+    stage_python(force)
     if available() and not force:
         return True
     os.makedirs(os.path.join(OUT, "shim", "THC"), exist_ok=True)

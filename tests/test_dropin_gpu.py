@@ -1,0 +1,254 @@
+"""Drop-in check: the reference's UNMODIFIED Python (pointnet2_utils.py, pointnet2_modules.py, iou3d_nms_utils.py,
+roiaware_pool3d_utils.py, model_nms_utils.py, box_utils.py -- staged byte for byte into oracle/_ref/py by
+oracle/build_ref.py) is executed twice on the same seeded inputs: once over `de6d_b200.compat.install()` (this
+library's kernels behind the reference's extension-module names) and once over the reference's own extension modules
+(oracle/_ref/*.so).  Sampled indices, new_xyz, counts, grouped features and the SA modules' outputs must be
+bit-identical; IoUs within 1e-5 relative; NMS selections identical.
+
+Follows: pointnet2_modules.py:358-494 (_PointnetSAModuleFSBase.forward), :141-167 (PointnetFPModule.forward),
+pointnet2_utils.py:10-488, iou3d_nms_utils.py:12-116, roiaware_pool3d_utils.py:9-41, model_nms_utils.py:6-25.
+"""
+import warnings
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL_IOU = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pair():
+    from oracle import build_ref, ref_py
+    if not (build_ref.available() and ref_py.available()):
+        pytest.skip("oracle/_ref (reference build + staged python) not present")
+    warnings.filterwarnings("ignore")           # legacy torch.cuda.FloatTensor constructors, escape sequences
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return ref_py.load_pair()
+
+
+def _cloud(b, n, seed, dup=0.0):
+    rng = np.random.default_rng(seed)
+    p = np.stack([rng.uniform(0, 35.2, (b, n)), rng.uniform(-20, 20, (b, n)), rng.uniform(-3, 1, (b, n))], -1).astype(np.float32)
+    if dup > 0:     # sample_points pads short frames by repeating points (data_processor.py:170-176): FPS ties
+        k = int(n * dup)
+        p[:, n - k:] = p[:, :k]
+    return torch.from_numpy(p).cuda()
+
+
+def _twin(pair, build):
+    """The same module built from both trees with identical parameters."""
+    ours, theirs = pair
+    torch.manual_seed(1234)
+    a = build(ours.pointnet2_modules).cuda()
+    torch.manual_seed(1234)
+    b = build(theirs.pointnet2_modules).cuda()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.equal(pa, pb)
+    return a, b
+
+
+def _same(x, y, what):
+    if x is None or y is None:
+        assert x is None and y is None, what
+        return
+    assert x.shape == y.shape and x.dtype == y.dtype, what
+    assert torch.equal(x, y), "%s differs: %d of %d elements" % (what, int((x != y).sum()), x.numel())
+
+
+def test_modules_really_are_the_reference_files(pair):
+    ours, theirs = pair
+    import de6d_b200.compat.pointnet2_batch_cuda as c
+    assert ours.pointnet2_utils.pointnet2 is c
+    assert theirs.pointnet2_utils.pointnet2.__file__.endswith("oracle/_ref/pointnet2_batch_cuda.so")
+    assert ours.pointnet2_utils.__file__ == theirs.pointnet2_utils.__file__       # same source file, two module objects
+    assert "oracle/_ref/py/pcdet" in ours.pointnet2_modules.__file__
+    assert ours.pointnet2_modules is not theirs.pointnet2_modules
+
+
+SA_LAYERS = [
+    # (name, N, C_in, kwargs, needs scores)
+    ("l1_dfps", 4096, 1, dict(npoint_list=[1024], sample_range_list=[[0, -1]], sample_method_list=["d-fps"],
+                              radii=[0.4, 0.8, 1.6], nsamples=[16, 16, 32], mlps=[[1, 16, 32], [1, 16, 32], [1, 16, 32]],
+                              aggregation_mlp=[64], confidence_mlp=[32]), False),
+    ("l2_ffps_dfps", 1024, 64, dict(npoint_list=[256, 256], sample_range_list=[[0, 1024], [0, 1024]],
+                                    sample_method_list=["f-fps", "d-fps"], radii=[0.8, 1.6], nsamples=[16, 32],
+                                    mlps=[[64, 32, 64], [64, 32, 64]], aggregation_mlp=[128], confidence_mlp=[64]), False),
+    ("l3_sfps_dfps", 512, 32, dict(npoint_list=[128, 128], sample_range_list=[[0, 256], [256, 512]],
+                                   sample_method_list=["s-fps", "d-fps"], radii=[1.6, 4.8], nsamples=[16, 32],
+                                   mlps=[[32, 32, 64], [32, 32, 64]], aggregation_mlp=[64], confidence_mlp=None,
+                                   weight_gamma=2.0), True),
+    ("dilated_skip", 1024, 16, dict(npoint_list=[256], sample_range_list=[[0, 1024]], sample_method_list=["d-fps"],
+                                    radii=[0.8, 1.6], nsamples=[16, 16], mlps=[[16, 32], [16, 32]], dilated_radius_group=True,
+                                    skip_connection=True, aggregation_mlp=[64], confidence_mlp=[16]), False),
+]
+
+
+@pytest.mark.parametrize("name,n,c_in,kw,needs_scores", SA_LAYERS, ids=[x[0] for x in SA_LAYERS])
+@pytest.mark.parametrize("dup", [0.0, 0.1], ids=["distinct", "padded"])
+def test_sa_module_forward_identical(pair, name, n, c_in, kw, needs_scores, dup):
+    """PointnetSAModuleFSMSG.forward (eval mode) over compat == over the reference extension, bit for bit."""
+    import copy
+    a, b = _twin(pair, lambda m: m.PointnetSAModuleFSMSG(**copy.deepcopy(kw)))
+    a.eval(); b.eval()
+    B = 3
+    xyz = _cloud(B, n, seed=hash(name) % 1000, dup=dup)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    feats = torch.randn(B, c_in, n, device="cuda", generator=g)
+    scores = torch.randn(B, n, device="cuda", generator=g) if needs_scores else None
+    with torch.no_grad():
+        oa = a(xyz, feats, scores=scores)
+        ob = b(xyz, feats, scores=scores)
+        for x, y, what in zip(oa, ob, ("new_xyz", "new_features", "new_scores")):
+            _same(x, y, "%s %s" % (name, what))
+        # the groupers on their own: idx_cnt and the (B, 3+C, npoint, nsample) tensor
+        new_xyz = oa[0]
+        for ga, gb in zip(a.groupers, b.groupers):
+            ca, fa = ga(xyz, new_xyz, feats)
+            cb, fb = gb(xyz, new_xyz, feats)
+            _same(ca, cb, name + " idx_cnt")
+            _same(fa, fb, name + " grouped features")
+    assert (oa[0][:, 0] == xyz[:, kw["sample_range_list"][0][0]]).all() or kw["sample_method_list"][0] != "d-fps"
+
+
+def test_sa_module_given_new_xyz(pair):
+    """The head's call form: new_xyz passed in (vote centres), no sampling (point_head_box6d_vote.py:846)."""
+    a, b = _twin(pair, lambda m: m.PointnetSAModuleFSMSG(radii=[4.8, 6.4], nsamples=[16, 32], mlps=[[32, 64], [32, 64]],
+                                                         aggregation_mlp=[64], confidence_mlp=None))
+    a.eval(); b.eval()
+    xyz = _cloud(2, 512, 5)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    feats = torch.randn(2, 32, 512, device="cuda", generator=g)
+    votes = (xyz[:, :128] + 0.5 * torch.randn(2, 128, 3, device="cuda", generator=g)).contiguous()
+    with torch.no_grad():
+        for x, y, what in zip(a(xyz, feats, new_xyz=votes), b(xyz, feats, new_xyz=votes), ("new_xyz", "new_features", "scores")):
+            _same(x, y, what)
+
+
+def test_sa_module_training_backward(pair):
+    """Training mode: forward identical, gradients (atomicAdd scatter in both builds) equal to accumulation-order noise."""
+    kw = dict(npoint_list=[128, 128], sample_range_list=[[0, 512], [0, 512]], sample_method_list=["d-fps", "s-fps"],
+              radii=[1.6, 3.2], nsamples=[16, 32], mlps=[[16, 32], [16, 32]], skip_connection=True,
+              aggregation_mlp=[64], confidence_mlp=[16])
+    import copy
+    a, b = _twin(pair, lambda m: m.PointnetSAModuleFSMSG(**copy.deepcopy(kw)))
+    a.train(); b.train()
+    xyz = _cloud(2, 512, 11)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    f0 = torch.randn(2, 16, 512, device="cuda", generator=g)
+    scores = torch.randn(2, 512, device="cuda", generator=g)
+    grads = []
+    for mod in (a, b):
+        f = f0.clone().requires_grad_(True)
+        new_xyz, nf, ns = mod(xyz, f, scores=scores)
+        (nf.square().mean() + ns.mean()).backward()
+        grads.append((new_xyz.detach(), nf.detach(), f.grad.clone(), [p.grad.clone() for p in mod.parameters()]))
+    _same(grads[0][0], grads[1][0], "new_xyz")
+    _same(grads[0][1], grads[1][1], "new_features (train)")
+    assert torch.allclose(grads[0][2], grads[1][2], rtol=1e-4, atol=1e-6)
+    for pa, pb in zip(grads[0][3], grads[1][3]):
+        assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6)
+
+
+def test_fp_module_and_plain_query_and_group(pair):
+    """PointnetFPModule (three_nn + three_interpolate) and QueryAndGroup / GroupAll through the reference wrappers."""
+    ours, theirs = pair
+    a, b = _twin(pair, lambda m: m.PointnetFPModule(mlp=[32 + 16, 32]))
+    a.eval(); b.eval()
+    unknown, known = _cloud(2, 2048, 21), _cloud(2, 512, 22)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    uf = torch.randn(2, 16, 2048, device="cuda", generator=g)
+    kf = torch.randn(2, 32, 512, device="cuda", generator=g)
+    with torch.no_grad():
+        _same(a(unknown, known, uf, kf), b(unknown, known, uf, kf), "FP module output")
+        da, ia = ours.pointnet2_utils.three_nn(unknown, known)
+        db, ib = theirs.pointnet2_utils.three_nn(unknown, known)
+        _same(ia, ib, "three_nn idx"); _same(da, db, "three_nn dist")
+        for r, ns in ((0.8, 16), (3.2, 64)):
+            qa = ours.pointnet2_utils.QueryAndGroup(r, ns)(unknown, known, uf)
+            qb = theirs.pointnet2_utils.QueryAndGroup(r, ns)(unknown, known, uf)
+            _same(qa, qb, "QueryAndGroup r=%g" % r)
+        _same(ours.pointnet2_utils.GroupAll()(unknown, None, uf), theirs.pointnet2_utils.GroupAll()(unknown, None, uf), "GroupAll")
+    # autograd through the reference Functions: gather / group / interpolate backward
+    for fn in ("gather_operation", "grouping_operation"):
+        outs = []
+        for tree in (ours, theirs):
+            f = kf.clone().requires_grad_(True)
+            if fn == "gather_operation":
+                idx = torch.randint(0, 512, (2, 300), device="cuda", generator=g, dtype=torch.int32) if not outs else idx
+                y = tree.pointnet2_utils.gather_operation(f, idx)
+            else:
+                idx = torch.randint(0, 512, (2, 100, 8), device="cuda", generator=g, dtype=torch.int32) if not outs else idx
+                y = tree.pointnet2_utils.grouping_operation(f, idx)
+            (y * y).sum().backward()
+            outs.append((y.detach(), f.grad))
+        _same(outs[0][0], outs[1][0], fn)
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-6), fn + " grad"
+
+
+def _boxes(n, seed, cluster=8):
+    rng = np.random.default_rng(seed)
+    k = max(1, n // cluster)
+    c = np.stack([rng.uniform(0, 70, k), rng.uniform(-40, 40, k), rng.uniform(-1.5, -0.5, k)], -1)
+    ctr = np.repeat(c, cluster, 0)[:n] + rng.normal(0, 0.3, (n, 3)) * [1, 1, 0.2]
+    dims = np.clip(rng.normal((3.9, 1.6, 1.56), 0.2, (n, 3)), 0.1, None)
+    yaw = np.repeat(rng.uniform(-np.pi, np.pi, k), cluster)[:n] + rng.normal(0, 0.1, n)
+    return torch.from_numpy(np.concatenate([ctr, dims, yaw[:, None]], 1).astype(np.float32)).cuda()
+
+
+def test_iou_wrappers(pair):
+    ours, theirs = pair
+    a, b = _boxes(300, 1), _boxes(200, 2)
+    for fn in ("boxes_iou_bev", "boxes_iou3d_gpu"):
+        x, y = getattr(ours.iou3d_nms_utils, fn)(a, b), getattr(theirs.iou3d_nms_utils, fn)(a, b)
+        assert ((x > 0) == (y > 0)).all(), fn
+        assert torch.allclose(x, y, rtol=RTOL_IOU, atol=1e-7), fn
+    x = ours.iou3d_nms_utils.boxes_bev_iou_cpu(a.cpu().numpy(), b.cpu().numpy())
+    y = theirs.iou3d_nms_utils.boxes_bev_iou_cpu(a.cpu().numpy(), b.cpu().numpy())
+    np.testing.assert_array_equal(x, y)          # host arithmetic on both sides: bit-identical
+    pts = _cloud(2, 4096, 3)
+    bx = torch.stack([_boxes(64, 4), _boxes(64, 5)])
+    _same(ours.roiaware_pool3d_utils.points_in_boxes_gpu(pts, bx), theirs.roiaware_pool3d_utils.points_in_boxes_gpu(pts, bx),
+          "points_in_boxes_gpu")
+    _same(ours.roiaware_pool3d_utils.points_in_boxes_cpu(pts[0].cpu(), bx[0].cpu()),
+          theirs.roiaware_pool3d_utils.points_in_boxes_cpu(pts[0].cpu(), bx[0].cpu()), "points_in_boxes_cpu")
+    # box_utils.remove_points_in_boxes3d (box_utils.py:92-107) runs on points_in_boxes_cpu
+    pa = ours.box_utils.remove_points_in_boxes3d(pts[0].cpu().numpy(), bx[0].cpu().numpy())
+    pb = theirs.box_utils.remove_points_in_boxes3d(pts[0].cpu().numpy(), bx[0].cpu().numpy())
+    np.testing.assert_array_equal(pa, pb)
+
+
+def _no_near_threshold(theirs, boxes, thresh, margin=1e-4):
+    iou = theirs.iou3d_nms_utils.boxes_iou_bev(boxes, boxes)
+    return not bool(((iou - thresh).abs() < margin).any())
+
+
+@pytest.mark.parametrize("nms_type", ["nms_gpu", "nms_normal_gpu"])
+def test_nms_and_class_agnostic_nms(pair, nms_type):
+    """iou3d_nms_utils.nms_gpu / nms_normal_gpu and model_nms_utils.class_agnostic_nms (the post_processing call,
+    detector3d_template.py:257-261) select the same boxes over both backends."""
+    ours, theirs = pair
+    checked = 0
+    for seed in range(12):
+        boxes = _boxes(512, 100 + seed)
+        scores = torch.rand(512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed))
+        for thresh in (0.01, 0.1, 0.7):
+            if nms_type == "nms_gpu" and not _no_near_threshold(theirs, boxes, thresh):
+                continue
+            ka, na = getattr(ours.iou3d_nms_utils, nms_type)(boxes, scores, thresh)
+            kb, nb = getattr(theirs.iou3d_nms_utils, nms_type)(boxes, scores, thresh)
+            assert na is None and nb is None
+            _same(ka, kb, "%s keep, seed %d thresh %g" % (nms_type, seed, thresh))
+            cfg = SimpleNamespace(NMS_TYPE=nms_type, NMS_THRESH=thresh, NMS_PRE_MAXSIZE=400, NMS_POST_MAXSIZE=100)
+            preds = torch.cat([boxes, torch.zeros(512, 2, device="cuda")], 1)       # 9-DoF predictions, sliced [:, 0:7]
+            sa, va = ours.model_nms_utils.class_agnostic_nms(scores, preds, cfg, score_thresh=0.1)
+            sb, vb = theirs.model_nms_utils.class_agnostic_nms(scores, preds, cfg, score_thresh=0.1)
+            _same(sa, sb, "class_agnostic_nms selected"); _same(va, vb, "class_agnostic_nms scores")
+            checked += 1
+    assert checked >= 12
