@@ -30,10 +30,14 @@ PROTOTYPES = {
     "de6d_ball_query_cnt": [_i, _i, _i, _f, _i, _p, _p, _p, _p, _p],
     "de6d_ball_query_dilated": [_i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p],
     "de6d_ball_query_workspace_bytes": [_i, _i],
+    "de6d_ball_query_grid_bytes": [_i, _i],
+    "de6d_ball_query_grid_build": [_i, _i, _f, _p, _p, _sz, _p],
     "de6d_ball_query_ex": [_i, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _sz, _p],
     "de6d_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_group_points_impl": [_i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     "de6d_group_concat": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "de6d_group_concat_t": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "de6d_gather_xyz": [_i, _i, _i, _p, _p, _p, _p, _p],
     "de6d_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
     "de6d_three_nn_ex": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p],
@@ -59,6 +63,7 @@ PROTOTYPES = {
 _RESTYPES = {
     "de6d_nms_workspace_bytes": _sz,
     "de6d_ball_query_workspace_bytes": _sz,
+    "de6d_ball_query_grid_bytes": _sz,
     "de6d_last_error_string": C.c_char_p,
     "de6d_build_info": C.c_char_p,
     "de6d_launch_count": C.c_longlong,

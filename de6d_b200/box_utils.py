@@ -27,9 +27,10 @@ def points_in_boxes3d_batched(points, boxes3d):
     """points (B, n, 3), boxes3d (B, m, 9) CUDA float32 -> (B, n) int64, one launch for the whole batch."""
     assert points.is_cuda and boxes3d.is_cuda and points.dtype == torch.float32 and boxes3d.dtype == torch.float32
     assert points.shape[0] == boxes3d.shape[0] and points.shape[2] == 3 and boxes3d.shape[2] == 9
+    from .compat._common import dev, stream_ptr
     points, boxes3d = points.contiguous(), boxes3d.contiguous()
     B, n, _ = points.shape
     out = torch.empty((B, n), dtype=torch.int64, device=points.device)
-    call("de6d_points_in_boxes9", B, boxes3d.shape[1], n, boxes3d.data_ptr(), points.data_ptr(), out.data_ptr(),
-         torch.cuda.current_stream().cuda_stream)
+    call("de6d_points_in_boxes9", B, boxes3d.shape[1], n, dev(boxes3d, "boxes3d", torch.float32), dev(points, "points", torch.float32),
+         out.data_ptr(), stream_ptr())
     return out

@@ -48,9 +48,18 @@ class ChainConfig:
     n_proposals: int = 512
     nms_thresh: float = 0.01
     ffps_gamma: float = 1.0
+    cloud: str = "uniform"                    # synthetic generator: "uniform" (KITTI crop) | "lidar" (64-beam rings)
 
     def name(self):
         return "sasa-3dssd-chain-%d" % self.n_points
+
+
+def stress_config():
+    """BASELINE.json configs[4]: 131072-point 64-beam LiDAR frames, D-FPS to 16384, ball_query ns = 64 + grouping
+    (one SA layer, C = 1; no head, no NMS)."""
+    return ChainConfig(n_points=131072, cloud="lidar",
+                       layers=[SALayer((16384,), ('d-fps',), ((0, 131072),), (0.2,), (64,), 1)],
+                       n_votes=0, vote_radii=(), vote_nsamples=(), n_proposals=0)
 
 
 def small_config():
@@ -69,7 +78,7 @@ def make_inputs(cfg: ChainConfig, batch: int, seed: int = 0, pinned: bool = True
     """Host-side inputs of one step (numpy-seeded, identical on every machine)."""
     from . import synth
     import numpy as np
-    xyz = synth.clouds(batch, cfg.n_points, seed)
+    xyz = (synth.lidar_clouds if cfg.cloud == "lidar" else synth.clouds)(batch, cfg.n_points, seed)
     feats = [synth.features(batch, cfg.layers[0].c_in, cfg.n_points, seed)]
     n_in = cfg.n_points
     scores = []
@@ -79,10 +88,12 @@ def make_inputs(cfg: ChainConfig, batch: int, seed: int = 0, pinned: bool = True
             feats.append(synth.features(batch, cfg.layers[li + 1].c_in, n_out, seed + 10 * (li + 1)))
         scores.append(synth.weights(batch, n_in, seed + 77 + li))   # S-FPS weights = sigmoid(score) ** gamma
         n_in = n_out
-    vote_feats = synth.features(batch, cfg.vote_c_in, n_in, seed + 99)
-    vote_offsets = np.random.default_rng(seed + 5).normal(0, 0.5, size=(batch, cfg.n_votes, 3)).astype(np.float32)
-    boxes, box_scores = synth.proposals(batch, cfg.n_proposals, seed)
-    host = {"xyz": xyz, "vote_feats": vote_feats, "vote_offsets": vote_offsets, "boxes": boxes, "box_scores": box_scores}
+    host = {"xyz": xyz}
+    if cfg.n_votes > 0:
+        host["vote_feats"] = synth.features(batch, cfg.vote_c_in, n_in, seed + 99)
+        host["vote_offsets"] = np.random.default_rng(seed + 5).normal(0, 0.5, size=(batch, cfg.n_votes, 3)).astype(np.float32)
+    if cfg.n_proposals > 0:
+        host["boxes"], host["box_scores"] = synth.proposals(batch, cfg.n_proposals, seed)
     for i, f in enumerate(feats):
         host["feats%d" % i] = f
     for i, s in enumerate(scores):
@@ -106,13 +117,18 @@ class OpChain:
 
     def __init__(self, cfg: ChainConfig, batch: int, device: Optional[torch.device] = None, use_graph: bool = True,
                  keep_matrices: bool = False, serial: bool = False, fused_group: bool = True,
-                 fused_ffps: bool = True):
+                 fused_ffps: bool = True, ffps: Optional[str] = None, shared_grid: bool = True):
         self.cfg, self.batch = cfg, batch
         self.keep_matrices = keep_matrices   # tests: expose the F-FPS distance matrices fed to the kernel
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.use_graph = use_graph
         self.fused_group = fused_group
-        self.fused_ffps = fused_ffps
+        # F-FPS route: "fused" (no (B,N,N) matrix; direct-difference metric), "matrix" (this library's matrix kernel + FPS
+        # kernel, same metric, same indices as "fused"), "cdist" (torch.cdist + FPS kernel = the reference pipeline: its
+        # fp32 GEMM-expansion metric, bit-identical indices to the reference on the same GPU)
+        self.ffps = ffps or ("fused" if fused_ffps else "matrix")
+        self.shared_grid = shared_grid
+        self._grids = {}
         self.main = torch.cuda.Stream(self.device)
         if serial:   # everything on one stream (per-kernel timing pass of bench.py, ncu launch lists)
             self.side = [self.main] * self.N_SIDE
@@ -131,7 +147,9 @@ class OpChain:
     def _alloc_like(self, host):
         with torch.cuda.device(self.device):
             self.inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
-            self.nms = BatchedNMS(self.batch, self.cfg.n_proposals, device=self.device)
+            if self.cfg.n_proposals > 0:
+                with torch.cuda.stream(self.main):     # the workspace is zeroed on the stream the kernel will run on
+                    self.nms = BatchedNMS(self.batch, self.cfg.n_proposals, device=self.device)
 
     SENSOR_KEYS = ("xyz", "feats0")   # what a deployment copies per frame: points + intensity
 
@@ -148,19 +166,21 @@ class OpChain:
         return sum(v.numel() * v.element_size() for k, v in self.inputs.items() if keys is None or k in keys)
 
     # ---- the chain --------------------------------------------------------------------------------
-    def _group_scales(self, xyz, new_xyz, feats, radii, nsamples, after, outs, tag):
-        """One QueryWithCntAndGroup per radius scale, scales spread over the side streams."""
+    def _group_scales(self, xyz, xyz_t, new_xyz, feats, radii, nsamples, after, outs, tag):
+        """One QueryWithCntAndGroup per radius scale, scales spread over the side streams.  The scales share one
+        ball-query grid of `xyz` (built on the main stream before `after`) and the transposed cloud `xyz_t`."""
         done = []
+        grid = self._grids.get(tag)
         for si, (r, ns) in enumerate(zip(radii, nsamples)):
             st = self.side[si % self.N_SIDE]
             st.wait_event(after)
             with torch.cuda.stream(st):
-                idx_cnt, idx = pu.ball_query_cnt(r, ns, xyz, new_xyz)
+                idx_cnt, idx = pu.ball_query_cnt(r, ns, xyz, new_xyz, grid=grid)
                 if self.fused_group:      # QueryWithCntAndGroup's tail as one pass (what pu.QueryWithCntAndGroup runs)
-                    new_features = pu.group_concat(xyz, new_xyz, feats, idx)
+                    new_features = pu.group_concat(xyz, new_xyz, feats, idx, xyz_t=xyz_t)
                 else:                     # the reference's op-by-op composition (pointnet2_utils.py:410-417)
-                    xyz_t = xyz.transpose(1, 2).contiguous()
-                    g_xyz = pu.grouping_operation(xyz_t, idx)
+                    xyz_tr = xyz.transpose(1, 2).contiguous()
+                    g_xyz = pu.grouping_operation(xyz_tr, idx)
                     g_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
                     g_feat = pu.grouping_operation(feats, idx)
                     new_features = torch.cat([g_xyz, g_feat], dim=1)
@@ -171,14 +191,28 @@ class OpChain:
                 done.append(ev)
         return done
 
+    def _sampled_xyz(self, xyz, sample_idx):
+        """new_xyz (B, M, 3) and its transposed copy (B, 3, M) for the next layer's grouping."""
+        if self.fused_group:
+            return pu.gather_xyz(xyz, sample_idx, want_transposed=True)
+        xyz_flipped = xyz.transpose(1, 2).contiguous()                 # the reference's sequence (pointnet2_modules.py:374,451-454)
+        new_t = pu.gather_operation(xyz_flipped, sample_idx)
+        return new_t.transpose(1, 2).contiguous(), new_t
+
+    def _build_grid(self, tag, xyz, radii):
+        """Called on the main stream right before the `after` event of _group_scales."""
+        self._grids[tag] = pu.BallQueryGrid(xyz, min(radii)) if (self.shared_grid and pu.BallQueryGrid.wanted(xyz.size(1))) else None
+
     def _forward(self):
         cfg, inp = self.cfg, self.inputs
         outs = {}
         main = self.main
         xyz = inp["xyz"]
+        self._grids = {}
         grouped_done: List[torch.cuda.Event] = []
         pending: List[torch.cuda.Event] = []   # every side-stream event main has not joined yet
         with torch.cuda.stream(main):
+            xyz_t = pu.gather_xyz(xyz, None)[1] if self.fused_group else None   # (B, 3, N) once per step
             for li, layer in enumerate(cfg.layers):
                 feats = inp["feats%d" % li]
                 scores = inp["scores%d" % li]
@@ -200,9 +234,13 @@ class OpChain:
                             sidx = pu.furthest_point_sample(xyz_slice, npnt)
                         elif method == "f-fps":
                             f_slice = feats[:, :, lo:hi].permute(0, 2, 1)
-                            if self.fused_ffps and not self.keep_matrices:
+                            if self.ffps == "fused" and not self.keep_matrices:
                                 sidx = pu.furthest_point_sample_features(xyz_slice, f_slice, cfg.ffps_gamma, npnt)
-                            else:   # the reference's call pair (pointnet2_modules.py:383-388)
+                            elif self.ffps == "cdist":   # exactly the reference's call pair (pointnet2_modules.py:383-388)
+                                mat = torch.cdist(xyz_slice, xyz_slice)
+                                mat += torch.cdist(f_slice, f_slice) * cfg.ffps_gamma
+                                sidx = pu.furthest_point_sample_matrix(mat, npnt)
+                            else:   # the call pair with this library's direct-difference matrix kernel
                                 mat = pu.calc_dist_matrix_for_sampling(xyz_slice, f_slice, cfg.ffps_gamma)
                                 sidx = pu.furthest_point_sample_matrix(mat, npnt)
                                 if self.keep_matrices:
@@ -221,27 +259,33 @@ class OpChain:
                 for ev in joins:
                     main.wait_event(ev)
                 sample_idx = torch.cat(idx_parts, dim=-1)
-                xyz_flipped = xyz.transpose(1, 2).contiguous()
-                new_xyz = pu.gather_operation(xyz_flipped, sample_idx).transpose(1, 2).contiguous()
+                new_xyz, new_xyz_t = self._sampled_xyz(xyz, sample_idx)
                 outs["l%d_idx" % li] = sample_idx
                 outs["l%d_new_xyz" % li] = new_xyz   # also keeps the block alive while side streams read it
+                if layer.radii:
+                    self._build_grid("l%d" % li, xyz, layer.radii)
                 sampled = torch.cuda.Event()
                 sampled.record(main)
-                grouped_done = self._group_scales(xyz, new_xyz, feats, layer.radii, layer.nsamples, sampled, outs, "l%d" % li)
+                grouped_done = self._group_scales(xyz, xyz_t, new_xyz, feats, layer.radii, layer.nsamples, sampled, outs, "l%d" % li)
                 pending.extend(grouped_done)
-                xyz = new_xyz
+                outs["l%d_xyz_t" % li] = xyz_t       # keeps the block alive while side streams read it
+                xyz, xyz_t = new_xyz, (new_xyz_t if self.fused_group else None)
             # head: vote centres grouped over the last layer's points (after its features exist)
             for ev in pending:
                 main.wait_event(ev)
-            votes = (xyz[:, :cfg.n_votes, :] + inp["vote_offsets"]).contiguous()
-            outs["votes"] = votes
-            ready = torch.cuda.Event()
-            ready.record(main)
-            head_done = self._group_scales(xyz, votes, inp["vote_feats"], cfg.vote_radii, cfg.vote_nsamples, ready, outs, "head")
-            for ev in head_done:
-                main.wait_event(ev)
-            keep, num = self.nms(inp["boxes"], inp["box_scores"], cfg.nms_thresh)
-            outs["nms_keep"], outs["nms_num"] = keep, num
+            if cfg.n_votes > 0:
+                votes = (xyz[:, :cfg.n_votes, :] + inp["vote_offsets"]).contiguous()
+                outs["votes"] = votes
+                self._build_grid("head", xyz, cfg.vote_radii)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                head_done = self._group_scales(xyz, xyz_t, votes, inp["vote_feats"], cfg.vote_radii, cfg.vote_nsamples, ready, outs, "head")
+                outs["head_xyz_t"] = xyz_t
+                for ev in head_done:
+                    main.wait_event(ev)
+            if cfg.n_proposals > 0:
+                keep, num = self.nms(inp["boxes"], inp["box_scores"], cfg.nms_thresh)
+                outs["nms_keep"], outs["nms_num"] = keep, num
         return outs
 
     def capture(self):
@@ -272,8 +316,10 @@ class OpChain:
     def result_tensors(self):
         """What a caller reads back per step: sampled indices of the last layer and the detections kept."""
         last = len(self.cfg.layers) - 1
-        return {"sample_idx": self.outputs["l%d_idx" % last], "nms_keep": self.outputs["nms_keep"],
-                "nms_num": self.outputs["nms_num"]}
+        res = {"sample_idx": self.outputs["l%d_idx" % last]}
+        if self.cfg.n_proposals > 0:
+            res["nms_keep"], res["nms_num"] = self.outputs["nms_keep"], self.outputs["nms_num"]
+        return res
 
     def d2h_bytes(self):
         return sum(v.numel() * v.element_size() for v in self.result_tensors().values())

@@ -9,17 +9,31 @@ from ._common import call, dev, need, stream_ptr
 f32, i32 = torch.float32, torch.int32
 
 
-def _ball_query(mode, b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, impl=0):
+def _ball_query(mode, b, n, m, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, impl=0, grid_ws=None):
     """All three variants go through de6d_ball_query_ex with scratch from torch's allocator (stream-ordered on the
-    current stream, CUDA-graph capturable)."""
+    current stream, CUDA-graph capturable).  grid_ws: a workspace tensor de6d_ball_query_grid_build already filled for
+    this `xyz` (BallQueryGrid in pointnet2_utils) -- the query then skips its own grid build (impl 3)."""
     need(new_xyz, b * m * 3, "new_xyz"); need(xyz, b * n * 3, "xyz"); need(idx, b * m * nsample, "idx")
     if idx_cnt is not None:
         need(idx_cnt, b * m, "idx_cnt")
-    ws_bytes = int(load().de6d_ball_query_workspace_bytes(b, n)) if impl == 0 else 0
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device) if ws_bytes else None
+    if grid_ws is not None:
+        impl, ws, ws_bytes = 3, grid_ws, grid_ws.numel()
+        if ws_bytes < int(load().de6d_ball_query_grid_bytes(b, n)) or ws.device != xyz.device:
+            raise ValueError("ball query grid workspace does not belong to a (%d, %d, 3) cloud batch on %s" % (b, n, xyz.device))
+    else:
+        ws_bytes = int(load().de6d_ball_query_workspace_bytes(b, n)) if impl == 0 else 0
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device) if ws_bytes else None
     call("de6d_ball_query_ex", mode, impl, b, n, m, radius_in, radius_out, nsample, dev(new_xyz, "new_xyz", f32),
          dev(xyz, "xyz", f32), None if idx_cnt is None else dev(idx_cnt, "idx_cnt", i32), dev(idx, "idx", i32),
          None if ws is None else ws.data_ptr(), ws_bytes, stream_ptr())
+    return 1
+
+
+def ball_query_grid_build(b, n, radius, xyz, workspace):
+    """Extension of this package: fill `workspace` (uint8, de6d_ball_query_grid_bytes(b, n)) with the search grid of xyz."""
+    need(xyz, b * n * 3, "xyz")
+    call("de6d_ball_query_grid_build", b, n, float(radius), dev(xyz, "xyz", f32), dev(workspace, "workspace", torch.uint8),
+         workspace.numel(), stream_ptr())
     return 1
 
 

@@ -521,6 +521,18 @@ three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown, const floa
 
 constexpr int BQG_MIN_N = 2048;   // below this the brute-force kernel is already cheap
 
+// One uniform grid per cloud over `xyz` with cells no smaller than the padded radius `r_abs` (and at most the cell cap).
+// The query kernel derives its cell range from the query's padded cube, so a grid built for radius r serves every
+// radius (a larger ball simply spans more cells): the radius scales of one SA layer share one grid.
+static int bq_build_grid(int b, int n, float r_abs, const float *xyz, void *ws, size_t per, cudaStream_t s) {
+    static unsigned long long dev_build = 0;
+    if (int rc = de6d_ensure_smem(bq_grid_build_kernel<false>, BQG_CAP * 4, dev_build, "ball_query grid smem attribute")) return rc;
+    if (n > BQG_BIG_N) bq_grid_build_kernel<true><<<b, BQG_BUILD_T, 0, s>>>(n, r_abs, BQG_CAP_BIG, xyz, reinterpret_cast<unsigned char *>(ws), per);
+    else bq_grid_build_kernel<false><<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, BQG_CAP, xyz, reinterpret_cast<unsigned char *>(ws), per);
+    DE6D_CHECK_LAUNCH("bq_grid_build_kernel");
+    return DE6D_OK;
+}
+
 template <int MODE>
 static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int nsample, const float *new_xyz,
                              const float *xyz, int *idx_cnt, int *idx, int impl, void *workspace,
@@ -535,12 +547,13 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
 
     const size_t list_smem = (size_t)BQG_QT * (size_t)((nsample | 1)) * sizeof(int);
     bool grid_ok = n > 0 && nsample > 0 && list_smem <= 160 * 1024;
-    bool use_grid = grid_ok && (impl == 2 || (impl == 0 && n >= BQG_MIN_N));
-    if (impl == 2 && !grid_ok) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: grid kernel not applicable");
+    bool use_grid = grid_ok && (impl == 2 || impl == 3 || (impl == 0 && n >= BQG_MIN_N));
+    if ((impl == 2 || impl == 3) && !grid_ok) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: grid kernel not applicable");
     if (use_grid) {
         const size_t per = bqg_ws_per_cloud(n), need = per * (size_t)b;
         void *ws = workspace;
         bool own = false;
+        if (impl == 3 && !ws) return de6d_set_error(DE6D_ERR_INVALID, "ball_query: impl 3 needs the workspace de6d_ball_query_grid_build filled");
         if (!ws) {   // raw C callers without a workspace: stream-ordered scratch
             cudaError_t e = cudaMallocAsync(&ws, need, s);
             if (e != cudaSuccess) return de6d_set_cuda_error(e, "ball_query workspace");
@@ -548,13 +561,11 @@ static int launch_ball_query(int b, int n, int m, float r_in, float r_out, int n
         } else if (workspace_bytes < need) {
             return de6d_set_error(DE6D_ERR_INVALID, "ball_query: workspace too small");
         }
-        static unsigned long long dev_build = 0, dev_query = 0;   // per call site (one per MODE instantiation)
-        if (int rc = de6d_ensure_smem(bq_grid_build_kernel<false>, BQG_CAP * 4, dev_build, "ball_query grid smem attribute")) return rc;
+        static unsigned long long dev_query = 0;   // per call site (one per MODE instantiation)
         if (int rc = de6d_ensure_smem(bq_grid_query_kernel<MODE>, 160 * 1024, dev_query, "ball_query query smem attribute")) return rc;
         const float r_abs = fabsf(r_out);
-        if (n > BQG_BIG_N) bq_grid_build_kernel<true><<<b, BQG_BUILD_T, 0, s>>>(n, r_abs, BQG_CAP_BIG, xyz, reinterpret_cast<unsigned char *>(ws), per);
-        else bq_grid_build_kernel<false><<<b, BQG_BUILD_T, BQG_CAP * 4, s>>>(n, r_abs, BQG_CAP, xyz, reinterpret_cast<unsigned char *>(ws), per);
-        DE6D_CHECK_LAUNCH("bq_grid_build_kernel");
+        if (impl != 3)   // impl 3: the grid in `workspace` was built by de6d_ball_query_grid_build (shared by several radii)
+            if (int rc = bq_build_grid(b, n, r_abs, xyz, ws, per, s)) return rc;
         double lim = 3.0 * sqrt((double)nsample * (double)n);
         if (lim < 1024.0) lim = 1024.0;
         if (lim > 2.0e9) lim = 2.0e9;
@@ -633,8 +644,27 @@ extern "C" size_t de6d_ball_query_workspace_bytes(int b, int n) {
     return bqg_ws_per_cloud(n) * (size_t)b;
 }
 
+// Build the search grid of `b` clouds once, for use by several de6d_ball_query_ex(..., impl = 3, ...) calls on the same
+// `xyz` (e.g. the radius scales of one SA layer, pointnet2_modules.py:462: three groupers, one cloud).  `radius`: the
+// SMALLEST radius that will be queried (cells are no smaller than it; any radius is answered exactly).
+extern "C" int de6d_ball_query_grid_build(int b, int n, float radius, const float *xyz, void *workspace, size_t workspace_bytes,
+                                          cudaStream_t stream) {
+    if (b < 0 || n < 0) return de6d_set_error(DE6D_ERR_INVALID, "ball_query_grid_build: negative size");
+    if (b == 0 || n == 0) return DE6D_OK;
+    if (!xyz || !workspace) return de6d_set_error(DE6D_ERR_INVALID, "ball_query_grid_build: null pointer");
+    if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "ball_query_grid_build: batch > 65535");
+    const size_t per = bqg_ws_per_cloud(n);
+    if (workspace_bytes < per * (size_t)b) return de6d_set_error(DE6D_ERR_INVALID, "ball_query_grid_build: workspace too small");
+    return bq_build_grid(b, n, fabsf(radius), xyz, workspace, per, stream);
+}
+// Bytes de6d_ball_query_grid_build needs for (b, n) -- unlike de6d_ball_query_workspace_bytes not 0 for small clouds.
+extern "C" size_t de6d_ball_query_grid_bytes(int b, int n) {
+    if (b <= 0 || n <= 0) return 0;
+    return bqg_ws_per_cloud(n) * (size_t)b;
+}
+
 // mode: 0 plain (ball_query), 1 counted (ball_query_cnt), 2 dilated.  impl: 0 auto, 1 brute-force kernel, 2 grid
-// kernel.  workspace: de6d_ball_query_workspace_bytes(b, n) bytes of device scratch, or NULL (the grid path then
+// kernel (builds its grid), 3 grid kernel over the grid de6d_ball_query_grid_build left in `workspace`.  workspace: de6d_ball_query_workspace_bytes(b, n) bytes of device scratch, or NULL (the grid path then
 // takes stream-ordered scratch from cudaMallocAsync).
 extern "C" int de6d_ball_query_ex(int mode, int impl, int b, int n, int m, float radius_in, float radius_out, int nsample,
                                   const float *new_xyz, const float *xyz, int *idx_cnt, int *idx, void *workspace,

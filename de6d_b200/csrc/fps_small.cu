@@ -107,13 +107,15 @@ fps_small_kernel(int b, int n, int m, int log2B, int C, int cinv, const float *_
     if (ww == 0 && lane == 0) idxs[0] = old;
 
     // weights below 1e-11 take the reference's double-precision key (fps.cu: sfps_key); they are rare, so the loop is
-    // compiled twice and the choice is warp-uniform
+    // compiled twice and the choice is uniform over the cloud's warps
     bool slow = false;
     if (MODE == 1) {
         bool mine = false;
 #pragma unroll
         for (int jj = 0; jj < RPL; ++jj) mine |= !(wt[jj] >= 1e-11f) && t[jj] != -INFINITY;
-        slow = __any_sync(0xffffffffu, mine);
+        // uniform over all warps of the cloud: the two instantiations of the loop below hold different bar.sync
+        // instructions, and the warps of one cloud must meet at the same one (compute-sanitizer synccheck, r2)
+        slow = W > 1 ? (__syncthreads_or(mine ? 1 : 0) != 0) : __any_sync(0xffffffffu, mine);
     }
     // in-lane arg-max in register (= tie) order, as NQ independent strict-'>' scans merged in order: a later segment
     // only replaces an earlier one when strictly larger, so the first maximum still wins

@@ -18,11 +18,23 @@ namespace de6d {
 
 constexpr int GS_THREADS = 512;
 
-// grid: (chunks, ceil(C/G), B).  Dynamic smem: G*n_pad floats + one mbarrier.
-template <bool TMA>
+// Leading coordinate rows of the fused grouper tail (de6d_group_concat): virtual rows 0..2 of the output are
+// xyz[idx] - new_xyz, rows 3.. are the feature channels.  A coordinate row is staged from the transposed cloud xyz_t
+// (b,3,n) by TMA when the caller has one, else from the AoS cloud with strided loads (served by L2: clouds are small).
+struct GroupXyz {
+    const float *xyz;       // (b, n, 3)
+    const float *xyz_t;     // (b, 3, n) or nullptr
+    const float *new_xyz;   // (b, m, 3) ball centres
+    int ns;                 // nsample: output slot j belongs to centre j / ns
+    int m;
+};
+
+// grid: (chunks, ceil(C/G), B).  Dynamic smem: G*n_pad floats + one mbarrier.  XYZ: the first 3 of the `c` rows are the
+// coordinate rows described above and `points` holds the remaining c - 3 channels (ns % 4 == 0 required).
+template <bool TMA, bool XYZ>
 __global__ void __launch_bounds__(GS_THREADS)
 group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chunk, const float *__restrict__ points,
-                    const int *__restrict__ idx, float *__restrict__ out, long long out_bstride) {
+                    const int *__restrict__ idx, float *__restrict__ out, long long out_bstride, GroupXyz gx) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     float *rows = reinterpret_cast<float *>(smem_raw + 128);
@@ -30,7 +42,14 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
     const int bs = blockIdx.z;
     const int c0 = blockIdx.y * G;
     const int g_here = min(G, c - c0);
-    const float *src = points + ((size_t)bs * c + c0) * n;
+    const int nx = XYZ ? 3 : 0;
+    const float *feat = points + (size_t)bs * (c - nx) * n;   // channel v >= nx lives at feat + (v - nx) * n
+
+    // where virtual row v comes from: TMA-able contiguous row, or nullptr = strided from the AoS cloud
+    auto row_src = [&](int v) -> const float * {
+        if (!XYZ || v >= nx) return feat + (size_t)(v - nx) * n;
+        return gx.xyz_t ? gx.xyz_t + ((size_t)bs * 3 + v) * n : nullptr;
+    };
 
     if (TMA) {
         if (threadIdx.x == 0) {
@@ -39,26 +58,47 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, (uint32_t)g_here * (uint32_t)n * 4u);
-            for (int g = 0; g < g_here; ++g) tma_bulk_g2s(rows + (size_t)g * n_pad, src + (size_t)g * n, (uint32_t)n * 4u, bar);
+            int nt = 0;
+            for (int g = 0; g < g_here; ++g) nt += row_src(c0 + g) != nullptr;
+            mbar_expect_tx(bar, (uint32_t)nt * (uint32_t)n * 4u);
+            for (int g = 0; g < g_here; ++g) {
+                const float *src = row_src(c0 + g);
+                if (src) tma_bulk_g2s(rows + (size_t)g * n_pad, src, (uint32_t)n * 4u, bar);
+            }
         }
-        mbar_wait(bar, 0);
-    } else {
-        for (int g = 0; g < g_here; ++g)
-            for (int i = threadIdx.x; i < n; i += GS_THREADS) rows[(size_t)g * n_pad + i] = src[(size_t)g * n + i];
-        __syncthreads();
     }
+    bool plain = false;   // rows this CTA copies with ordinary loads
+    for (int g = 0; g < g_here; ++g) {
+        const float *src = row_src(c0 + g);
+        if (TMA && src) continue;
+        plain = true;
+        float *dstrow = rows + (size_t)g * n_pad;
+        if (src) {
+            for (int i = threadIdx.x; i < n; i += GS_THREADS) dstrow[i] = src[i];
+        } else {
+            const float *a = gx.xyz + (size_t)bs * n * 3 + (c0 + g);
+            for (int i = threadIdx.x; i < n; i += GS_THREADS) dstrow[i] = __ldg(a + (size_t)i * 3);
+        }
+    }
+    if (plain || !TMA) __syncthreads();   // `plain` is uniform over the CTA
+    if (TMA) mbar_wait(bar, 0);
 
     const long long j0 = (long long)blockIdx.x * chunk;
     const long long j1 = min(ms, j0 + chunk);
     const int *ix = idx + (size_t)bs * ms;
     float *dst = out + (size_t)bs * out_bstride + (size_t)c0 * ms;
+    const float *ctr = XYZ ? gx.new_xyz + (size_t)bs * gx.m * 3 : nullptr;
     // chunk is a multiple of 4 and ms % 4 == 0 is checked by the host for this kernel
     for (long long j = j0 + 4ll * threadIdx.x; j < j1; j += 4ll * GS_THREADS) {
         const int4 k = ldg_stream_int4(ix + j);
+        const unsigned q = XYZ ? (unsigned)j / (unsigned)gx.ns : 0u;   // ms < 2^31 checked by the host; 4 slots share a centre
         for (int g = 0; g < g_here; ++g) {
             const float *r = rows + (size_t)g * n_pad;
             float4 v = make_float4(r[k.x], r[k.y], r[k.z], r[k.w]);
+            if (XYZ) {   // branch-free: channel rows subtract +0.0f, which leaves every float (incl. -0, NaN payloads aside) as is
+                const float cv = (c0 + g < nx) ? __ldg(ctr + (size_t)q * 3 + (c0 + g)) : 0.f;
+                v.x = __fsub_rn(v.x, cv); v.y = __fsub_rn(v.y, cv); v.z = __fsub_rn(v.z, cv); v.w = __fsub_rn(v.w, cv);
+            }
             stg_stream_float4(dst + (size_t)g * ms + j, v);
         }
     }
@@ -159,11 +199,15 @@ group_xyz_center_kernel(int n, int m, int ns, int vec, const float *__restrict__
     }
 }
 
+// c counts the 3 coordinate rows when gx != nullptr (points then holds c - 3 channels); returns DE6D_OK and sets
+// *launched = false when the staged kernel is not applicable to the coordinate rows (caller takes the two-kernel path).
 static int group_forward(int b, int c, int n, long long ms, const float *points, const int *idx, float *out,
-                         long long out_bstride, int force_impl, cudaStream_t s) {
+                         long long out_bstride, int force_impl, cudaStream_t s, const GroupXyz *gx = nullptr,
+                         bool *launched = nullptr) {
+    if (launched) *launched = false;
     if (b < 0 || c < 0 || n < 0 || ms < 0) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: negative size");
     if (b == 0 || c == 0 || ms == 0) return DE6D_OK;
-    if (!points || !idx || !out) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: null pointer");
+    if ((!points && !(gx && c == 3)) || !idx || !out) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: null pointer");
     if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "group/gather: batch > 65535");
 
     // staged kernel: rows must fit, outputs per row must amortise the staging, 16-byte alignment everywhere
@@ -171,7 +215,8 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
     const int n_pad = (n + 3) & ~3;
     const bool aligned = (ms % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const bool tma_ok = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    bool tma_ok = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) & 15) == 0);
+    if (gx && gx->xyz_t) tma_ok = tma_ok && ((reinterpret_cast<uintptr_t>(gx->xyz_t) & 15) == 0);
     // channel rows per CTA: as many as fit in ~64 KB (three CTAs per SM hide the index-load latency better than one
     // CTA with 192 KB: measured +3..10 % on B200, scripts/group_tune.py), at most 8, at least one if a row fits at all
     int G = (int)(smem_budget / ((size_t)n_pad * 4 + 1));
@@ -181,9 +226,13 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
     if (G > c) G = c;
     if (G > 8) G = 8;
     bool staged = aligned && G >= 1 && ms >= 2ll * n;
-    if (force_impl == 1) staged = false;
-    if (force_impl == 2 && !(aligned && G >= 1)) return de6d_set_error(DE6D_ERR_INVALID, "group: staged kernel not applicable");
-    if (force_impl == 2) staged = true;
+    if (gx) {
+        if (!(staged && gx->ns % 4 == 0 && ms < (1ll << 31))) return DE6D_OK;   // not launched: caller falls back
+    } else {
+        if (force_impl == 1) staged = false;
+        if (force_impl == 2 && !(aligned && G >= 1)) return de6d_set_error(DE6D_ERR_INVALID, "group: staged kernel not applicable");
+        if (force_impl == 2) staged = true;
+    }
 
     if (staged) {
         const int cgroups = ceil_div(c, G);
@@ -197,16 +246,21 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
         chunk = (chunk + 3) & ~3ll;
         chunks = ceil_div_ll(ms, chunk);
         size_t smem = 128 + (size_t)G * n_pad * 4;
-        static unsigned long long devs[2] = {0, 0};
-        if (smem > 48 * 1024) {
-            int rc = tma_ok ? de6d_ensure_smem(group_staged_kernel<true>, 208 * 1024, devs[1], "group smem attribute")
-                            : de6d_ensure_smem(group_staged_kernel<false>, 208 * 1024, devs[0], "group smem attribute");
-            if (rc) return rc;
-        }
+        static unsigned long long devs[4] = {0, 0, 0, 0};
         dim3 grid((unsigned)chunks, cgroups, b);
-        if (tma_ok) group_staged_kernel<true><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride);
-        else group_staged_kernel<false><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride);
+        const GroupXyz none = {nullptr, nullptr, nullptr, 4, 0};
+#define DE6D_GROUP_LAUNCH(T, X, slot)                                                                                          \
+    do {                                                                                                                       \
+        if (smem > 48 * 1024)                                                                                                  \
+            if (int rc = de6d_ensure_smem(group_staged_kernel<T, X>, 208 * 1024, devs[slot], "group smem attribute")) return rc; \
+        group_staged_kernel<T, X><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride,     \
+                                                                  gx ? *gx : none);                                            \
+    } while (0)
+        if (gx) { if (tma_ok) DE6D_GROUP_LAUNCH(true, true, 3); else DE6D_GROUP_LAUNCH(false, true, 2); }
+        else { if (tma_ok) DE6D_GROUP_LAUNCH(true, false, 1); else DE6D_GROUP_LAUNCH(false, false, 0); }
+#undef DE6D_GROUP_LAUNCH
         DE6D_CHECK_LAUNCH("group_staged_kernel");
+        if (launched) *launched = true;
         return DE6D_OK;
     }
     constexpr int CPT = 4;
@@ -265,14 +319,24 @@ extern "C" int de6d_gather_points_grad(int b, int c, int n, int npoints, const f
 // for use_xyz = True: out (b, 3 + c, npoints, nsample) = cat(xyz[idx] - new_xyz, features[idx]) written once, instead of
 // transpose + group + in-place subtract + group + torch.cat (three extra passes over the largest tensor of the network).
 // xyz (b,n,3), new_xyz (b,npoints,3), features (b,c,n) or NULL with c == 0, idx (b,npoints,nsample).
-extern "C" int de6d_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
-                                 const float *features, const int *idx, float *out, cudaStream_t stream) {
+// xyz_t: optional transposed copy of xyz, (b,3,n) (the reference module keeps one as `xyz_flipped`,
+// pointnet2_modules.py:374): coordinate rows are then staged by TMA like feature rows; NULL = staged from xyz itself.
+// One launch (coordinates and channels are rows of the same shared-memory staged kernel) whenever nsample % 4 == 0 and the
+// output is 16-byte aligned; other shapes take a coordinate kernel + the channel kernel.
+extern "C" int de6d_group_concat_t(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *xyz_t,
+                                   const float *new_xyz, const float *features, const int *idx, float *out, cudaStream_t stream) {
     if (b < 0 || c < 0 || n < 0 || npoints < 0 || nsample < 0) return de6d_set_error(DE6D_ERR_INVALID, "group_concat: negative size");
     const long long ms = (long long)npoints * nsample;
     if (b == 0 || ms == 0) return DE6D_OK;
     if (!xyz || !new_xyz || !idx || !out || (c > 0 && !features)) return de6d_set_error(DE6D_ERR_INVALID, "group_concat: null pointer");
     if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "group_concat: batch > 65535");
     const long long bstride = (long long)(3 + c) * ms;
+    {
+        const GroupXyz gx = {xyz, xyz_t, new_xyz, nsample, npoints};
+        bool launched = false;
+        if (int rc = group_forward(b, 3 + c, n, ms, features, idx, out, bstride, 0, stream, &gx, &launched)) return rc;
+        if (launched) return DE6D_OK;
+    }
     const int vec = (nsample % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     long long work = vec ? ms / 4 : ms;
     long long bx = ceil_div_ll(work, 256);
@@ -281,5 +345,45 @@ extern "C" int de6d_group_concat(int b, int c, int n, int npoints, int nsample, 
     group_xyz_center_kernel<<<grid, 256, 0, stream>>>(n, npoints, nsample, vec, xyz, new_xyz, idx, out, bstride);
     DE6D_CHECK_LAUNCH("group_xyz_center_kernel");
     if (c > 0) return group_forward(b, c, n, ms, features, idx, out + 3 * ms, bstride, 0, stream);
+    return DE6D_OK;
+}
+extern "C" int de6d_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
+                                 const float *features, const int *idx, float *out, cudaStream_t stream) {
+    return de6d_group_concat_t(b, c, n, npoints, nsample, xyz, nullptr, new_xyz, features, idx, out, stream);
+}
+
+// new_xyz = xyz[sample_idx] in both layouts with one launch: replaces transpose(1,2).contiguous() -> gather_operation ->
+// transpose(1,2).contiguous() of the SA module (pointnet2_modules.py:374,451-454).  xyz (b,n,3), idx (b,m) or NULL
+// (identity: m == n, plain transposition), new_xyz (b,m,3) and/or new_xyz_t (b,3,m), either may be NULL.
+namespace de6d {
+__global__ void __launch_bounds__(256)
+gather_xyz_kernel(int n, int m, const float *__restrict__ xyz, const int *__restrict__ idx, float *__restrict__ new_xyz,
+                  float *__restrict__ new_xyz_t) {
+    const int bs = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= m) return;
+    const int k = idx ? idx[(size_t)bs * m + j] : j;
+    const float *p = xyz + ((size_t)bs * n + k) * 3;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    if (new_xyz) {
+        float *o = new_xyz + ((size_t)bs * m + j) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
+    }
+    if (new_xyz_t) {
+        float *o = new_xyz_t + (size_t)bs * 3 * m + j;
+        o[0] = x; o[m] = y; o[2 * (size_t)m] = z;
+    }
+}
+}  // namespace de6d
+extern "C" int de6d_gather_xyz(int b, int n, int m, const float *xyz, const int *idx, float *new_xyz, float *new_xyz_t,
+                               cudaStream_t stream) {
+    if (b < 0 || n < 0 || m < 0) return de6d_set_error(DE6D_ERR_INVALID, "gather_xyz: negative size");
+    if (b == 0 || m == 0) return DE6D_OK;
+    if (!xyz || (!new_xyz && !new_xyz_t)) return de6d_set_error(DE6D_ERR_INVALID, "gather_xyz: null pointer");
+    if (!idx && m != n) return de6d_set_error(DE6D_ERR_INVALID, "gather_xyz: idx == NULL needs m == n");
+    if (b > 65535) return de6d_set_error(DE6D_ERR_INVALID, "gather_xyz: batch > 65535");
+    dim3 grid(ceil_div(m, 256), b);
+    gather_xyz_kernel<<<grid, 256, 0, stream>>>(n, m, xyz, idx, new_xyz, new_xyz_t);
+    DE6D_CHECK_LAUNCH("gather_xyz_kernel");
     return DE6D_OK;
 }

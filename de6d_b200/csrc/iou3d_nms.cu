@@ -364,7 +364,11 @@ nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ n
         }
         __syncthreads();
     }
-    if (tid == 0) num_keep[f] = nk;
+    // entries beyond num_keep are defined: position 0 (callers gather through the whole padded row)
+    __shared__ int s_nk;
+    if (tid == 0) { num_keep[f] = nk; s_nk = nk; }
+    __syncthreads();
+    for (int i = s_nk + tid; i < n; i += NMS_T) keep[i] = 0;
 }
 
 }  // namespace de6d

@@ -92,12 +92,19 @@ class BatchedNMS:
         else:
             order = scores.sort(1, descending=True)[1]
             sorted_boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, 7)).contiguous()
+        if nvalid is not None:
+            if not (nvalid.is_cuda and nvalid.dtype == torch.int32 and nvalid.is_contiguous() and nvalid.numel() == F
+                    and nvalid.device == boxes.device):
+                raise ValueError("nvalid must be a contiguous int32 tensor of %d elements on %s" % (F, boxes.device))
+        if not boxes.is_cuda or boxes.device != self.ws.device:
+            raise ValueError("boxes must live on %s" % self.ws.device)
         call("de6d_nms_batched", F, n, sorted_boxes.data_ptr(), None if nvalid is None else nvalid.data_ptr(),
              float(thresh), int(bool(normal)), self.keep_pos.data_ptr(), self.num.data_ptr(), self.ws.data_ptr(),
              self.ws_bytes, torch.cuda.current_stream().cuda_stream)
         if order is None:
             return self.keep_pos, self.num
-        # positions -> original indices; entries beyond num[f] are padding (position 0)
+        # positions -> original indices; entries beyond num[f] are padding: the kernel writes position 0 there, so the
+        # padded tail of the returned row repeats the frame's top-scoring box index
         return torch.gather(order, 1, self.keep_pos), self.num
 
 

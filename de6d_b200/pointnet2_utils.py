@@ -37,6 +37,17 @@ class FarthestPointSampling(Function):
 farthest_point_sample = furthest_point_sample = FarthestPointSampling.apply
 
 
+def _strided_features(features, B, N, device):
+    """(B, N, C) float32 CUDA view with arbitrary non-negative strides on `device` (the permuted (B, C, N) backbone tensor)."""
+    if not (isinstance(features, torch.Tensor) and features.is_cuda and features.dtype == torch.float32):
+        raise TypeError("features must be a float32 CUDA tensor")
+    if features.dim() != 3 or tuple(features.shape[:2]) != (B, N) or features.device != device:
+        raise ValueError("features must have shape (B, N, C) on the device of xyz")
+    if min(features.stride()) < 0:
+        raise ValueError("features must not have negative strides")
+    return features.data_ptr()
+
+
 @torch.no_grad()
 def calc_dist_matrix_for_sampling(xyz: torch.Tensor, features: torch.Tensor = None, gamma: float = 1.0):
     """F-FPS input (reference :36-44): pairwise L2 of coordinates plus gamma * pairwise L2 of features, (B, N, N).
@@ -44,18 +55,17 @@ def calc_dist_matrix_for_sampling(xyz: torch.Tensor, features: torch.Tensor = No
     direct differences instead of the reference's two torch.cdist (GEMM expansion) + scale + add passes; values
     agree with torch.cdist to its own rounding error (~1e-3 abs for close points, where the expansion cancels)."""
     from ._lib import call
+    from .compat._common import stream_ptr
     assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.dim() == 3 and xyz.size(2) == 3
     xyz = xyz.contiguous()
     B, N, _ = xyz.shape
+    px = _chk(xyz, "xyz", torch.float32)
     out = torch.empty((B, N, N), dtype=torch.float32, device=xyz.device)
     if features is not None:
-        assert features.is_cuda and features.dtype == torch.float32 and features.shape[:2] == (B, N)
-        sb, sn, sc = features.stride()
-        call("de6d_dist_matrix", B, N, features.size(2), xyz.data_ptr(), features.data_ptr(), sb, sn, sc, float(gamma),
-             out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        fptr, (sb, sn, sc) = _strided_features(features, B, N, xyz.device), features.stride()
+        call("de6d_dist_matrix", B, N, features.size(2), px, fptr, sb, sn, sc, float(gamma), out.data_ptr(), stream_ptr())
     else:
-        call("de6d_dist_matrix", B, N, 0, xyz.data_ptr(), None, 0, 0, 0, float(gamma), out.data_ptr(),
-             torch.cuda.current_stream().cuda_stream)
+        call("de6d_dist_matrix", B, N, 0, px, None, 0, 0, 0, float(gamma), out.data_ptr(), stream_ptr())
     return out
 
 
@@ -78,8 +88,9 @@ def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, ga
     One thread-block cluster (6 or 8 CTAs) per cloud evaluates only the selected rows out of distributed shared memory; shapes that do not
     fit on chip take the two-call form."""
     from ._lib import call, load
-    assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()
+    from .compat._common import stream_ptr
     B, N, _ = xyz.shape
+    px = _chk(xyz, "xyz", torch.float32, (B, N, 3))
     C = 0 if features is None else features.size(2)
     if not load().de6d_furthest_point_sampling_features_fits(N, C):
         return furthest_point_sample_matrix(calc_dist_matrix_for_sampling(xyz, features, gamma), npoint)
@@ -88,10 +99,9 @@ def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, ga
     if features is None:
         fptr, (sb, sn, sc) = None, (0, 0, 0)
     else:
-        assert features.is_cuda and features.dtype == torch.float32 and features.shape[:2] == (B, N)
-        fptr, (sb, sn, sc) = features.data_ptr(), features.stride()
-    call("de6d_furthest_point_sampling_features", B, N, C, npoint, xyz.data_ptr(), fptr, sb, sn, sc, float(gamma),
-         temp.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        fptr, (sb, sn, sc) = _strided_features(features, B, N, xyz.device), features.stride()
+    call("de6d_furthest_point_sampling_features", B, N, C, npoint, px, fptr, sb, sn, sc, float(gamma),
+         temp.data_ptr(), out.data_ptr(), stream_ptr())
     return out
 
 
@@ -233,21 +243,56 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
+class BallQueryGrid:
+    """Search grid of a batch of clouds, built once and shared by every ball query over the same `xyz` -- the radius
+    scales of one SA layer (pointnet2_modules.py:462-463 runs one grouper per scale on the same cloud).
+
+        grid = BallQueryGrid(xyz, min(radii))                         # one build kernel
+        idx_cnt, idx = ball_query_cnt(r, ns, xyz, new_xyz, grid=grid)   # per scale: query kernel only
+
+    Results are identical with and without a grid (tests/test_parity_gpu.py).  Clouds below 2048 points are answered by
+    the brute-force kernel, which needs no grid: `BallQueryGrid.wanted(n)` tells."""
+
+    MIN_N = 2048
+
+    @staticmethod
+    def wanted(n):
+        return n >= BallQueryGrid.MIN_N
+
+    def __init__(self, xyz: torch.Tensor, radius: float):
+        from ._lib import load
+        assert xyz.is_cuda and xyz.is_contiguous() and xyz.dtype == torch.float32 and xyz.dim() == 3 and xyz.size(2) == 3
+        self.b, self.n = xyz.size(0), xyz.size(1)
+        self.xyz_ptr = xyz.data_ptr()
+        self.ws = torch.empty(int(load().de6d_ball_query_grid_bytes(self.b, self.n)), dtype=torch.uint8, device=xyz.device)
+        _ext.ball_query_grid_build(self.b, self.n, radius, xyz, self.ws)
+
+    def check(self, xyz):
+        if xyz.data_ptr() != self.xyz_ptr or xyz.size(0) != self.b or xyz.size(1) != self.n:
+            raise ValueError("BallQueryGrid was built for a different xyz tensor")
+        return self.ws
+
+
 @torch.no_grad()
-def ball_query_cnt(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor):
-    """(reference :307-327) -> (idx_cnt (B, npoint), idx (B, npoint, nsample)); hit list repeated cyclically."""
+def ball_query_cnt(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor, grid: "BallQueryGrid" = None):
+    """(reference :307-327) -> (idx_cnt (B, npoint), idx (B, npoint, nsample)); hit list repeated cyclically.
+    grid (not in the reference): a BallQueryGrid of `xyz` to reuse."""
     assert new_xyz.is_contiguous()
     assert xyz.is_contiguous()
     B, N, _ = xyz.size()
     npoint = new_xyz.size(1)
     idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
     idx_cnt = torch.zeros((B, npoint), dtype=torch.int32, device=xyz.device)
-    _ext.ball_query_cnt_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx_cnt, idx)
+    if grid is None:
+        _ext.ball_query_cnt_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx_cnt, idx)
+    else:
+        _ext._ball_query(1, B, N, npoint, 0.0, radius, nsample, new_xyz, xyz, idx_cnt, idx, grid_ws=grid.check(xyz))
     return idx_cnt, idx
 
 
 @torch.no_grad()
-def ball_query_dilated(radius_in: float, radius_out: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor):
+def ball_query_dilated(radius_in: float, radius_out: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
+                       grid: "BallQueryGrid" = None):
     """(reference :330-351) shell radius_in <= d < radius_out."""
     assert new_xyz.is_contiguous()
     assert xyz.is_contiguous()
@@ -255,24 +300,62 @@ def ball_query_dilated(radius_in: float, radius_out: float, nsample: int, xyz: t
     npoint = new_xyz.size(1)
     idx_cnt = torch.zeros((B, npoint), dtype=torch.int32, device=xyz.device)
     idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
-    _ext.ball_query_dilated_wrapper(B, N, npoint, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx)
+    if grid is None:
+        _ext.ball_query_dilated_wrapper(B, N, npoint, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx)
+    else:
+        _ext._ball_query(2, B, N, npoint, radius_in, radius_out, nsample, new_xyz, xyz, idx_cnt, idx, grid_ws=grid.check(xyz))
     return idx_cnt, idx
 
 
-def group_concat(xyz, new_xyz, features, idx):
+def _chk(t, name, dtype, shape=None):
+    """CHECK_INPUT for the entry points that are not in the reference's pybind table: CUDA, contiguous, dtype, on the
+    current device (the kernel is launched on the current stream), optional exact shape.  Returns data_ptr()."""
+    from .compat._common import dev
+    ptr = dev(t, name, dtype)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return ptr
+
+
+def group_concat(xyz, new_xyz, features, idx, xyz_t=None):
     """cat(xyz[idx] - new_xyz, features[idx]) -> (B, 3 + C, npoint, nsample) in one kernel pass (no autograd).
-    Bit-identical to the reference composition: copies plus one fp32 subtraction."""
+    Bit-identical to the reference composition: copies plus one fp32 subtraction.  xyz_t: optional (B, 3, N) transposed
+    copy of xyz (the SA module's `xyz_flipped`): coordinate rows are then TMA-staged like the channels."""
     from ._lib import call
+    from .compat._common import stream_ptr
+    if xyz.dim() != 3 or idx.dim() != 3:
+        raise ValueError("group_concat: xyz (B, N, 3), idx (B, npoint, nsample)")
     B, N, _ = xyz.shape
     _, M, ns = idx.shape
     C = 0 if features is None else features.size(1)
     out = torch.empty((B, 3 + C, M, ns), dtype=torch.float32, device=xyz.device)
-    for t in (xyz, new_xyz, idx) + (() if features is None else (features,)):
-        assert t.is_cuda and t.is_contiguous()
-    call("de6d_group_concat", B, C, N, M, ns, xyz.data_ptr(), new_xyz.data_ptr(),
-         None if features is None else features.data_ptr(), idx.data_ptr(), out.data_ptr(),
-         torch.cuda.current_stream().cuda_stream)
+    call("de6d_group_concat_t", B, C, N, M, ns, _chk(xyz, "xyz", torch.float32, (B, N, 3)),
+         None if xyz_t is None else _chk(xyz_t, "xyz_t", torch.float32, (B, 3, N)),
+         _chk(new_xyz, "new_xyz", torch.float32, (B, M, 3)),
+         None if features is None else _chk(features, "features", torch.float32, (B, C, N)),
+         _chk(idx, "idx", torch.int32, (B, M, ns)), out.data_ptr(), stream_ptr())
     return out
+
+
+@torch.no_grad()
+def gather_xyz(xyz, sample_idx, want_transposed=False):
+    """new_xyz = xyz[sample_idx]: (B, N, 3), (B, M) int32 -> (B, M, 3) [and (B, 3, M)] with one launch instead of the SA
+    module's transpose -> gather_operation -> transpose (pointnet2_modules.py:374,451-454).  Pure copies.
+    sample_idx None: only the transposed copy of xyz itself is produced (returns (xyz, xyz_t))."""
+    from ._lib import call
+    from .compat._common import stream_ptr
+    B, N, _ = xyz.shape
+    px = _chk(xyz, "xyz", torch.float32, (B, N, 3))
+    if sample_idx is None:
+        xyz_t = torch.empty((B, 3, N), dtype=torch.float32, device=xyz.device)
+        call("de6d_gather_xyz", B, N, N, px, None, None, xyz_t.data_ptr(), stream_ptr())
+        return xyz, xyz_t
+    M = sample_idx.size(1)
+    new_xyz = torch.empty((B, M, 3), dtype=torch.float32, device=xyz.device)
+    new_t = torch.empty((B, 3, M), dtype=torch.float32, device=xyz.device) if want_transposed else None
+    call("de6d_gather_xyz", B, N, M, px, _chk(sample_idx, "sample_idx", torch.int32, (B, M)), new_xyz.data_ptr(),
+         None if new_t is None else new_t.data_ptr(), stream_ptr())
+    return (new_xyz, new_t) if want_transposed else new_xyz
 
 
 def _needs_grad(*ts):

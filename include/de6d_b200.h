@@ -112,11 +112,19 @@ int de6d_ball_query_dilated(int b, int n, int m, float radius_in, float radius_o
  * results, see csrc/ball_query.cu) and need device scratch, which they take from cudaMallocAsync on `stream`.
  * Hosts with their own allocator (the torch layer) use the explicit form instead:
  *   mode 0 = ball_query, 1 = ball_query_cnt, 2 = ball_query_dilated;  impl 0 = automatic, 1 = brute-force kernel,
- *   2 = grid kernel;  workspace = de6d_ball_query_workspace_bytes(b, n) bytes (0 = none needed) or NULL. */
+ *   2 = grid kernel;  workspace = de6d_ball_query_workspace_bytes(b, n) bytes (0 = none needed) or NULL;
+ *   impl 3 = grid kernel over a grid that de6d_ball_query_grid_build already left in `workspace`. */
 size_t de6d_ball_query_workspace_bytes(int b, int n);
 int de6d_ball_query_ex(int mode, int impl, int b, int n, int m, float radius_in, float radius_out, int nsample,
                        const float *new_xyz, const float *xyz, int *idx_cnt, int *idx, void *workspace,
                        size_t workspace_bytes, cudaStream_t stream);
+/* One search grid per cloud shared by several queries of the same `xyz`: the radius scales of an SA layer
+ * (pointnet2_modules.py:462-463 runs one QueryWithCntAndGroup per scale over the same cloud; the reference rescans all
+ * n points per scale).  radius = the smallest radius that will be queried; workspace = de6d_ball_query_grid_bytes(b, n)
+ * bytes.  Then call de6d_ball_query_ex(mode, 3, ...) once per scale with the same workspace. */
+size_t de6d_ball_query_grid_bytes(int b, int n);
+int de6d_ball_query_grid_build(int b, int n, float radius, const float *xyz, void *workspace, size_t workspace_bytes,
+                               cudaStream_t stream);
 
 /* ---- pointnet2_batch: grouping ------------------------------------------------------------------------ */
 
@@ -132,6 +140,15 @@ int de6d_group_points_impl(int b, int c, int n, int npoints, int nsample, const 
  * xyz (b,n,3), new_xyz (b,npoints,3), features (b,c,n) (NULL when c == 0), idx (b,npoints,nsample). */
 int de6d_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *new_xyz,
                       const float *features, const int *idx, float *out, cudaStream_t stream);
+/* The same with an optional transposed copy of the cloud, xyz_t (b,3,n) (`xyz_flipped` of pointnet2_modules.py:374):
+ * coordinate rows are then staged by TMA exactly like feature rows.  NULL = de6d_group_concat. */
+int de6d_group_concat_t(int b, int c, int n, int npoints, int nsample, const float *xyz, const float *xyz_t,
+                        const float *new_xyz, const float *features, const int *idx, float *out, cudaStream_t stream);
+/* new_xyz = xyz[sample_idx] in (b,m,3) and/or transposed (b,3,m) layout, one launch: replaces the SA module's
+ * transpose(1,2).contiguous() -> gather_operation -> transpose(1,2).contiguous() (pointnet2_modules.py:374,451-454).
+ * idx (b,m) or NULL (identity, m == n: plain transposition); either output may be NULL. */
+int de6d_gather_xyz(int b, int n, int m, const float *xyz, const int *idx, float *new_xyz, float *new_xyz_t,
+                    cudaStream_t stream);
 /* group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out, idx, grad_points)   group_points.cpp:18-27, group_points_gpu.cu:14-51 */
 int de6d_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
                            float *grad_points, cudaStream_t stream);

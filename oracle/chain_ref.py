@@ -61,12 +61,14 @@ def run_chain(cfg, host, frames=None, keep_groups=False, matrices=None, ffps_mat
             if keep_groups:
                 out["l%d_s%d" % (li, si)] = nf
         xyz = new_xyz
-    votes = np.ascontiguousarray(xyz[:, :cfg.n_votes] + h["vote_offsets"])
-    for si, (r, ns) in enumerate(zip(cfg.vote_radii, cfg.vote_nsamples)):
+    votes = np.ascontiguousarray(xyz[:, :cfg.n_votes] + h["vote_offsets"]) if cfg.n_votes > 0 else None
+    for si, (r, ns) in enumerate(zip(cfg.vote_radii, cfg.vote_nsamples) if cfg.n_votes > 0 else ()):
         cnt, nf = _group(xyz, votes, h["vote_feats"], r, ns)
         out["head_s%d_cnt" % si] = cnt
         if keep_groups:
             out["head_s%d" % si] = nf
+    if cfg.n_proposals <= 0:
+        return out
     F = h["boxes"].shape[0]
     keep = np.zeros((F, cfg.n_proposals), np.int64)
     num = np.zeros(F, np.int32)
