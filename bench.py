@@ -11,10 +11,17 @@ sharded across ranks with no data-path collective (weak scaling: 8 GPUs x 64 = c
 
 One JSON line on stdout (rank 0):
   value     frames/s, inputs resident in HBM, CUDA-graph replay, CUDA events on the launching stream, max over ranks
-  e2e       frames/s through OpChain.step_host: pinned host inputs -> H2D -> chain -> D2H of the results, every step
-  roofline  dominant kernel (by measured time) against the measured HBM peak; `kernels` lists every entry point
-  cpu_baseline  the oracle (CPU restatement of the reference kernels) on a bounded sample of the same workload
-oracle/ is used here only as that CPU baseline / the --impl reference arm, never on the measured GPU path.
+  e2e       frames/s through OpChain.step_host: pinned host sensor inputs (points + intensity) -> H2D -> chain -> D2H of
+            the results, every step; the stand-ins for tensors the detector's MLPs produce ON the device stay resident
+            (`e2e_all_inputs` copies those too, every step)
+  roofline  the HBM-bound kernel that moves most of the step's bytes against the measured HBM peak, and the kernel that
+            takes most of the step's time (issue/latency-bound sampling) as fraction of the GPU's issue slots;
+            `kernels` lists every entry point
+  cpu_baseline   the oracle (CPU restatement of the reference kernels) on a bounded sample of the same workload
+  reference_cuda the same chain issued op by op with the reference's OWN CUDA kernels (oracle/_ref, recompiled for sm_100)
+            through the reference's own python, on this GPU -- the yardstick SURVEY.md names; outside every timed region
+  other_configs  BASELINE.json configs[1] (16 frames) and configs[4] (131072-point stress frames), short runs
+oracle/ is used here only for cpu_baseline / reference_cuda / the --impl reference arm, never on the measured GPU path.
 """
 import argparse
 import json
@@ -92,10 +99,16 @@ def algorithmic_bytes(name, a):
     if name in ("de6d_group_points", "de6d_group_points_impl"):
         b, c, n, npnt, ns = a[0], a[1], a[2], a[3], a[4]
         return b * (4 * npnt * ns + 4 * c * min(n, npnt * ns) + 4 * c * npnt * ns)
-    if name == "de6d_group_concat":
+    if name in ("de6d_group_concat", "de6d_group_concat_t"):
         b, c, n, npnt, ns = a[0], a[1], a[2], a[3], a[4]
         touched = min(n, npnt * ns)
         return b * (4 * npnt * ns + 12 * touched + 12 * npnt + 4 * c * touched + 4 * (3 + c) * npnt * ns)
+    if name == "de6d_gather_xyz":
+        b, n, m = a[0], a[1], a[2]
+        return b * (4 * m + 12 * m + 12 * m + 12 * m)      # idx + gathered points read, both layouts written
+    if name == "de6d_ball_query_grid_build":
+        b, n = a[0], a[1]
+        return b * (12 * n + 16 * n)                        # cloud read, sorted records written
     if name == "de6d_nms_batched":
         frames, n = a[0], a[1]
         return frames * 36 * n
@@ -238,13 +251,34 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(args, batch, world, note=None):
+CONFIGS = {
+    # name: (BASELINE.json configs index, default frames per GPU)
+    "chain64": (2, 64),          # configs[2]; x8 GPUs = configs[3] (512 frames)
+    "chain16": (1, 16),          # configs[1]
+    "stress131072": (4, 4),      # configs[4]
+}
+
+
+def config_of(args):
     from de6d_b200 import chain as ch
-    cfg = ch.ChainConfig()
+    name = getattr(args, "config", "chain64")
+    cfg = ch.stress_config() if name == "stress131072" else ch.ChainConfig()
+    batch = args.batch if getattr(args, "batch", None) else CONFIGS[name][1]
+    return cfg, batch
+
+
+def workload_config(args, batch, world, note=None):
+    cfg, _ = config_of(args)
+    name = getattr(args, "config", "chain64")
+    if name == "stress131072":
+        what = ("large-cloud stress chain (BASELINE configs[4]): 131072-point 64-beam LiDAR frames, D-FPS 131072->16384 (8-CTA "
+                "cluster per cloud) + ball_query_cnt r=0.2 ns=64 + grouping; %d frames per GPU" % batch)
+    else:
+        what = ("Det6D/SASA SA chain 16384->4096->1024->512 (D-FPS+F-FPS+S-FPS, ball_query_cnt+group per scale) "
+                "+ vote grouping + rotated NMS on %d proposals/frame; %d frames per GPU (BASELINE configs[%d]%s)"
+                % (cfg.n_proposals, batch, CONFIGS[name][0], "; x8 GPUs = configs[3]" if name == "chain64" else ""))
     c = {
-        "workload": "Det6D/SASA SA chain 16384->4096->1024->512 (D-FPS+F-FPS+S-FPS, ball_query_cnt+group per scale) "
-                    "+ vote grouping + rotated NMS on %d proposals/frame; %d frames per GPU (BASELINE configs[2]; x8 GPUs = configs[3])"
-                    % (cfg.n_proposals, batch),
+        "workload": what, "name": name,
         "points_per_frame": cfg.n_points, "frames_per_gpu": batch, "global_frames": batch * world,
         "sharding": "frames x%d, no data-path collective" % world,
         "layers": [{"npoints": l.npoints, "methods": l.methods, "radii": l.radii, "nsamples": l.nsamples, "c_in": l.c_in}
@@ -257,6 +291,183 @@ def workload_config(args, batch, world, note=None):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def ncu_issue(entry, shape):
+    """Issue-slot statistics of the kernel behind a latency/issue-bound entry point from the committed ncu captures
+    (profiles/ncu_issue.json: issue-active fraction of the SMs that ran the kernel, SMs occupied, cycles per sample)."""
+    p = os.path.join(ROOT, "profiles", "ncu_issue.json")
+    try:
+        with open(p) as f:
+            tab = json.load(f)
+    except Exception:
+        return None
+    return tab.get(entry + ":" + ",".join(str(x) for x in shape))
+
+
+class ChainRunner:
+    """P independent chains (own static buffers, CUDA graph and streams) fed round-robin: step k+1 starts its latency-bound
+    sampling while step k is in its bandwidth-bound grouping.  All timing is CUDA events on a stream that fences every
+    chain's stream, between barriers, max over ranks."""
+
+    def __init__(self, cfg, batch, dev, P, rank, world, **chain_kw):
+        import torch
+        from de6d_b200 import chain as ch
+        self.torch, self.cfg, self.batch, self.dev, self.P, self.world = torch, cfg, batch, dev, P, world
+        self.hosts = [ch.make_inputs(cfg, batch, seed=rank * P + i) for i in range(P)]
+        self.chains = []
+        for i in range(P):
+            c = ch.OpChain(cfg, batch, device=dev, **chain_kw)
+            c.load(self.hosts[i])
+            c.capture()
+            self.chains.append(c)
+        self.tstream = torch.cuda.Stream(dev)
+        torch.cuda.synchronize()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, step_fn, steps):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.tstream)
+        for c in self.chains:
+            c.main.wait_event(e0)
+        for k in range(steps):
+            step_fn(k)
+        for c in self.chains:
+            ev = torch.cuda.Event()
+            ev.record(c.main)
+            self.tstream.wait_event(ev)
+        e1.record(self.tstream)
+        self.barrier()
+        return e0.elapsed_time(e1)
+
+    def resident(self, steps, warmup):
+        from de6d_b200 import dist as ddist
+        self.timed(lambda k: self.chains[k % self.P].step(), warmup)
+        return ddist.max_over_ranks(self.timed(lambda k: self.chains[k % self.P].step(), steps), self.dev)
+
+    def e2e(self, steps, keys):
+        from de6d_b200 import dist as ddist
+
+        def step(k):
+            c = self.chains[k % self.P]
+            c.main.synchronize()            # this chain's previous step is complete: its host results are readable
+            c.step_host(self.hosts[k % self.P], sync=False, keys=keys)
+        self.timed(step, 3)
+        return ddist.max_over_ranks(self.timed(step, steps), self.dev)
+
+
+def per_kernel_pass(cfg, batch, dev, host, reps=5):
+    """The same chain, one stream, eager, CUDA events around every C-ABI call.  Returns (kernels[], total ms per step)."""
+    import torch
+    from de6d_b200 import _lib, chain as ch
+    prof = ch.OpChain(cfg, batch, device=dev, use_graph=False, serial=True)
+    prof.load(host)
+    prof.capture()                      # eager warm-up (use_graph=False: nothing is captured)
+    torch.cuda.synchronize()
+    _lib.trace_begin()
+    for _ in range(reps):
+        prof.step()
+    trace = _lib.trace_end()
+    agg = {}
+    for name, a, t in trace:
+        shape = []
+        for x in a:                      # leading sizes / scalars of the C-ABI call, up to the first pointer
+            if x is None or (isinstance(x, int) and abs(x) >= (1 << 31)):
+                break
+            shape.append(round(x, 4) if isinstance(x, float) else x)
+        d = agg.setdefault((name, tuple(shape)), {"ms": 0.0, "launches": 0, "bytes": algorithmic_bytes(name, a)})
+        d["ms"] += t
+        d["launches"] += 1
+    peak, _ = measured_peaks()
+    kernels = []
+    for (name, shape), d in agg.items():
+        avg = d["ms"] / d["launches"]
+        gbs = d["bytes"] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+        kernels.append({"entry": name, "shape": list(shape), "ms_per_launch": round(avg, 5),
+                        "launches_per_step": d["launches"] // reps, "alg_bytes": d["bytes"],
+                        "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)})
+    kernels.sort(key=lambda k: -k["ms_per_launch"] * k["launches_per_step"])
+    total_ms = sum(k["ms_per_launch"] * k["launches_per_step"] for k in kernels)
+    del prof
+    return kernels, total_ms
+
+
+HBM_BOUND = ("de6d_group_points", "de6d_group_concat", "de6d_group_concat_t", "de6d_gather_points", "de6d_gather_xyz",
+             "de6d_furthest_point_sampling_matrix", "de6d_three_interpolate")
+
+
+def build_roofline(kernels, total_ms, step_ms):
+    """Top level: the HBM-bound kernel with the most algorithmic bytes per step (the roofline north_star targets at
+    >= 60 %), and -- as *_by_time -- the kernel with the most time per step, which is an issue/latency-bound sampling
+    kernel whose HBM fraction is meaningless (it reads its 12.6 MB once and then iterates on chip)."""
+    peak, peak_src = measured_peaks()
+    by_time = kernels[0]
+    hbm = [k for k in kernels if k["entry"] in HBM_BOUND]
+    by_bytes = max(hbm, key=lambda k: k["alg_bytes"] * k["launches_per_step"]) if hbm else by_time
+    step_bytes = sum(k["alg_bytes"] * k["launches_per_step"] for k in kernels)
+    r = {"kernel": by_bytes["entry"], "shape": by_bytes["shape"], "bound": "hbm", "achieved": by_bytes["gbs"], "peak": peak,
+         "unit": "GB/s", "frac": by_bytes["frac_hbm"], "traffic": ncu_traffic(by_bytes["entry"], by_bytes["shape"]),
+         "alg_bytes": by_bytes["alg_bytes"], "ms_per_launch": by_bytes["ms_per_launch"], "peak_source": peak_src,
+         "share_of_step_bytes": round(by_bytes["alg_bytes"] * by_bytes["launches_per_step"] / step_bytes, 4) if step_bytes else None,
+         "note": "dominant kernel by bytes; timed alone (single stream, eager) with CUDA events on its stream; "
+                 "achieved = algorithmic bytes / duration"}
+    hb = sum(k["alg_bytes"] * k["launches_per_step"] for k in hbm)
+    ht = sum(k["ms_per_launch"] * k["launches_per_step"] for k in hbm)
+    r["hbm_bound_kernels_all"] = {"alg_bytes_per_step": hb, "ms_per_step": round(ht, 4),
+                                  "gbs": round(hb / (ht * 1e-3) / 1e9, 1) if ht else None,
+                                  "frac": round(hb / (ht * 1e-3) / 1e9 / peak, 4) if ht else None,
+                                  "min_frac_over_group_rows": min([k["frac_hbm"] for k in hbm if k["entry"].startswith("de6d_group")] or [None])}
+    issue = ncu_issue(by_time["entry"], by_time["shape"]) or {}
+    r.update({"kernel_by_time": by_time["entry"], "shape_by_time": by_time["shape"], "bound_by_time": "issue",
+              "ms_per_launch_by_time": by_time["ms_per_launch"],
+              "share_of_step_time": round(by_time["ms_per_launch"] * by_time["launches_per_step"] / total_ms, 4) if total_ms else None,
+              "issue_active": issue.get("issue_active"), "sms_occupied": issue.get("sms_occupied"),
+              "frac_by_time": (round(issue["issue_active"] * issue["sms_occupied"] / 148.0, 4)
+                               if issue.get("issue_active") is not None and issue.get("sms_occupied") else None),
+              "cycles_per_sample": issue.get("cycles_per_sample"), "smem_wavefront_frac": issue.get("smem_wavefront_frac"),
+              "stalls": issue.get("stalls"), "issue_source": issue.get("source"),
+              "hbm_frac_by_time": by_time["frac_hbm"], "traffic_by_time": ncu_traffic(by_time["entry"], by_time["shape"]),
+              "note_by_time": "dominant kernel by time: latency/issue-bound (one CTA or cluster per cloud iterating on chip); "
+                              "frac_by_time = issue-active fraction x SMs occupied / 148 from the committed ncu capture"})
+    r["whole_step"] = {"alg_bytes": step_bytes, "ms_per_step_pipelined": round(step_ms, 4),
+                       "gbs": round(step_bytes / (step_ms * 1e-3) / 1e9, 1), "frac_hbm": round(step_bytes / (step_ms * 1e-3) / 1e9 / peak, 4)}
+    return r
+
+
+def reference_cuda_leg(cfg, batch, dev, chain):
+    """The yardstick SURVEY.md names: the reference's own CUDA kernels (oracle/_ref, compiled unmodified for sm_100)
+    driven by the reference's own python, op by op, on this GPU and these inputs.  Not part of any timed product region."""
+    try:
+        import warnings
+        warnings.filterwarnings("ignore")
+        from oracle import build_ref, ref_py, chain_ref_cuda
+        if not (build_ref.available() and ref_py.available()):
+            return {"unavailable": "oracle/_ref not built (needs /root/reference at build time)"}
+        import torch
+        tree = ref_py.load_tree("pcdet_ref", build_ref.load())
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.cuda.device(dev):
+            ms, ops = chain_ref_cuda.time_chain(cfg, chain.inputs, tree, steps=2, warmup=1)
+            ref, _ = chain_ref_cuda.run(cfg, chain.inputs, tree)
+            torch.cuda.synchronize()
+            same = {}
+            for k in ("l0_idx", "l1_idx", "l2_idx"):
+                if k in ref and k in chain.outputs:
+                    same[k] = round(float((ref[k] == chain.outputs[k]).float().mean()), 5)
+        return {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": round(ms, 3),
+                "per_op_ms": {k: round(v, 3) for k, v in sorted(ops.items(), key=lambda kv: -kv[1])},
+                "kind": "reference CUDA kernels recompiled for sm_100 (nvcc -O2), reference python wrappers, legacy default stream, "
+                        "host-synchronised wall clock over 2 passes",
+                "same_index_fraction_vs_product_chain": same}
+    except Exception as e:  # noqa: BLE001 -- a yardstick that cannot run must not take the bench line down
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -268,83 +479,33 @@ def run_gpu_arm(args):
         de6d_build.build()           # no-op when lib/libde6d_b200.so is newer than csrc/ (it travels with the repo)
     if world > 1:
         dist.barrier()               # the other ranks only load the library
-    from de6d_b200 import _lib, chain as ch
+    from de6d_b200 import chain as ch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the op chain has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    cfg = ch.ChainConfig()
-    batch = args.batch
+    cfg, batch = config_of(args)
     P = max(1, args.pipeline)
-    # P independent chains (own static buffers, CUDA graph and streams) fed round-robin: step k+1 starts its
-    # latency-bound sampling (one CTA per cloud, 64 of 148 SMs) while step k is in its bandwidth-bound grouping.
-    hosts = [ch.make_inputs(cfg, batch, seed=rank * P + i) for i in range(P)]
-    host = hosts[0]
-    chains = []
-    for i in range(P):
-        c = ch.OpChain(cfg, batch, device=dev)
-        c.load(hosts[i])
-        c.capture()
-        chains.append(c)
-    chain = chains[0]
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    run = ChainRunner(cfg, batch, dev, P, rank, world)
+    chain = run.chains[0]
     out_bytes = sum(v.numel() * v.element_size() for k, v in chain.outputs.items() if isinstance(v, torch.Tensor))
     clocks = ClockSampler(local)
-    tstream = torch.cuda.Stream(dev)
 
-    def timed(step_fn, steps):
-        """K steps over the P chains between two events on a timing stream that fences every chain's stream."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(tstream)
-        for c in chains:
-            c.main.wait_event(e0)
-        for k in range(steps):
-            step_fn(k)
-        for c in chains:
-            ev = torch.cuda.Event()
-            ev.record(c.main)
-            tstream.wait_event(ev)
-        e1.record(tstream)
-        barrier()
-        return e0.elapsed_time(e1)
-
-    # ---- device-resident timed region --------------------------------------------------------------------
+    # ---- device-resident timed region, then end to end (H2D of the sensor inputs + chain + D2H), every step ---------
     W = max(args.warmup, 3)
-    timed(lambda k: chains[k % P].step(), W)
+    run.timed(lambda k: run.chains[k % P].step(), W)
     clocks.start()
-    ms = ddist.max_over_ranks(timed(lambda k: chains[k % P].step(), args.steps), dev)
-
-    # ---- end to end: pinned host inputs -> H2D -> chain -> D2H, every step ------------------------------------
-    def e2e_step(k):
-        c = chains[k % P]
-        c.main.synchronize()            # this chain's previous step is complete: its host results are readable
-        c.step_host(hosts[k % P], sync=False)
-
-    timed(e2e_step, 3)
-    ms_e2e = ddist.max_over_ranks(timed(e2e_step, args.steps), dev)
-
-    def e2e_sensor_step(k):             # same, copying only what a deployment receives from the host per frame
-        c = chains[k % P]
-        c.main.synchronize()
-        c.step_host(hosts[k % P], sync=False, keys=ch.OpChain.SENSOR_KEYS)
-
-    timed(e2e_sensor_step, 3)
-    ms_e2e_sensor = ddist.max_over_ranks(timed(e2e_sensor_step, args.steps), dev)
+    ms = ddist.max_over_ranks(run.timed(lambda k: run.chains[k % P].step(), args.steps), dev)
+    ms_e2e = run.e2e(args.steps, ch.OpChain.SENSOR_KEYS)
     clocks.stop()
+    ms_e2e_all = run.e2e(args.steps, None)
     frames_global = batch * world
     # the one collective of the deployment: all ranks' padded keep lists gathered over NCCL (outside the timed regions)
     gather_ms = None
-    if world > 1:
+    if world > 1 and cfg.n_proposals > 0:
         keep, num = chain.outputs["nms_keep"], chain.outputs["nms_num"]
         ddist.gather_detections(keep, num)
-        barrier()
+        run.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         keep_all, num_all = ddist.gather_detections(keep, num)
@@ -353,80 +514,38 @@ def run_gpu_arm(args):
         assert keep_all.shape[0] == world * batch and num_all.shape[0] == world * batch
         gather_ms = g0.elapsed_time(g1)
 
-    # ---- per entry-point timing (rank 0): the same chain, one stream, eager, CUDA events around every launch -----
-    kernels, roofline, fps_us = [], None, None
+    line = None
     if rank == 0:
-        prof = ch.OpChain(cfg, batch, device=dev, use_graph=False, serial=True)
-        prof.load(host)
-        prof.capture()                      # eager warm-up (use_graph=False: nothing is captured)
-        torch.cuda.synchronize()
-        reps = 5
-        _lib.trace_begin()
-        for _ in range(reps):
-            prof.step()
-        trace = _lib.trace_end()
-        agg = {}
-        for name, a, t in trace:
-            shape = []
-            for x in a:                      # leading sizes / scalars of the C-ABI call, up to the first pointer
-                if x is None or (isinstance(x, int) and abs(x) >= (1 << 31)):
-                    break
-                shape.append(round(x, 4) if isinstance(x, float) else x)
-            key = (name, tuple(shape))
-            d = agg.setdefault(key, {"ms": 0.0, "launches": 0, "bytes": algorithmic_bytes(name, a)})
-            d["ms"] += t
-            d["launches"] += 1
-        peak, peak_src = measured_peaks()
-        by_name = {}
-        for (name, shape), d in agg.items():
-            avg = d["ms"] / d["launches"]
-            gbs = d["bytes"] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
-            kernels.append({"entry": name, "shape": list(shape), "ms_per_launch": round(avg, 5),
-                            "launches_per_step": d["launches"] // reps, "alg_bytes": d["bytes"],
-                            "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)})
-            by_name.setdefault(name, 0.0)
-            by_name[name] += d["ms"] / reps
-        kernels.sort(key=lambda k: -k["ms_per_launch"] * k["launches_per_step"])
-        total_ms = sum(by_name.values())
-        top = kernels[0]
-        roofline = {"kernel": top["entry"], "shape": top["shape"], "bound": "hbm", "achieved": top["gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": ncu_traffic(top["entry"], top["shape"]), "peak_source": peak_src,
-                    "ms_per_launch": top["ms_per_launch"],
-                    "share_of_step": round(top["ms_per_launch"] * top["launches_per_step"] / total_ms, 4) if total_ms else None,
-                    "note": "dominant entry point by time; timed alone (single stream, eager) with CUDA events on its stream"}
-        for k in kernels:   # the HBM-bound gather with the largest output: the >=60 %-of-roofline target of north_star
-            if k["entry"] in ("de6d_group_points", "de6d_group_concat"):
-                if "group_points" not in roofline or k["alg_bytes"] > roofline["group_points"]["alg_bytes"]:
-                    roofline["group_points"] = {"entry": k["entry"], "shape": k["shape"], "alg_bytes": k["alg_bytes"], "achieved": k["gbs"],
-                                                "frac": k["frac_hbm"], "ms_per_launch": k["ms_per_launch"],
-                                                "traffic": ncu_traffic(k["entry"], k["shape"])}
+        kernels, total_ms = per_kernel_pass(cfg, batch, dev, run.hosts[0])
+        roofline = build_roofline(kernels, total_ms, ms / args.steps)
+        fps_us = None
+        for k in kernels:
             if k["entry"] == "de6d_furthest_point_sampling" and k["shape"][1] == cfg.n_points:
                 fps_us = 1e3 * k["ms_per_launch"] / batch
-        del prof
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_single_core(args.cpu_seconds)
-
-    if rank == 0:
         line = {
             "metric": METRIC, "value": frames_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, batch, world,
                                       note="L2: per-step working set %.0f MB of inputs+outputs >> 126 MB L2, no explicit flush; "
-                                           "%d chains in flight (round-robin), every step a full pass over its own batch" % (
+                                           "%d chains in flight (round-robin), every step a full pass over its own batch. "
+                                           "F-FPS: the fused kernel evaluates the metric by direct differences, the reference "
+                                           "pipeline by torch.cdist's fp32 GEMM expansion -- same selected sets in >= 99.8 %%, same "
+                                           "position in >= 98.9 %% of the slots, and closer to the float64-exact greedy sequence than "
+                                           "the reference itself (profiles/r2_ffps_agreement.json); `value_ffps_reference_route` is "
+                                           "the chain with torch.cdist + matrix kernel (bit-identical to the reference)" % (
                                           (out_bytes + chain.h2d_bytes()) / 1e6, P)),
             "e2e": {"value": frames_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": chain.h2d_bytes(), "d2h_bytes_per_step": chain.d2h_bytes(),
+                    "h2d_bytes_per_step": chain.h2d_bytes(ch.OpChain.SENSOR_KEYS), "d2h_bytes_per_step": chain.d2h_bytes(),
                     "ms_per_step": ms_e2e / args.steps,
-                    "note": "every input tensor of the step is copied from pinned host memory each step, including the "
-                            "synthetic stand-ins for on-device MLP outputs (per-layer features, scores, proposals)"},
-            "e2e_sensor_inputs_only": {"value": frames_global * args.steps / (ms_e2e_sensor * 1e-3), "unit": UNIT,
-                                       "h2d_bytes_per_step": chain.h2d_bytes(ch.OpChain.SENSOR_KEYS),
-                                       "d2h_bytes_per_step": chain.d2h_bytes(), "ms_per_step": ms_e2e_sensor / args.steps,
-                                       "note": "H2D of points + intensity only (what the detector receives per frame); "
-                                               "the stand-ins for MLP outputs stay resident"},
+                    "note": "every step: H2D of the sensor inputs a deployment receives per frame (points + intensity) from pinned "
+                            "host memory, the chain, D2H of sampled indices + kept detections.  The per-layer features, S-FPS "
+                            "scores, vote features and proposals are outputs of the detector's MLPs / head ON the device "
+                            "(pointnet2_backbone.py:199-263); their synthetic stand-ins stay resident.  e2e_all_inputs copies them too"},
+            "e2e_all_inputs": {"value": frames_global * args.steps / (ms_e2e_all * 1e-3), "unit": UNIT,
+                               "h2d_bytes_per_step": chain.h2d_bytes(), "d2h_bytes_per_step": chain.d2h_bytes(),
+                               "ms_per_step": ms_e2e_all / args.steps,
+                               "note": "also copies the stand-ins for on-device MLP outputs every step (PCIe-bound)"},
             "gpu_launches": int(chain.kernels_per_step) * args.steps,
             "gpu_launches_note": "%d launches of this library's kernels per step (counted by de6d_launch_count on the eager "
                                  "warm-up pass) replayed from one CUDA graph per step" % chain.kernels_per_step,
@@ -434,9 +553,53 @@ def run_gpu_arm(args):
             "roofline": roofline,
             "fps_us_per_frame": fps_us,
             "kernels": kernels,
-            "cpu_baseline": cpu,
+            "serialized_kernel_ms_per_step": round(total_ms, 4),
             "detections_all_gather_ms": gather_ms,
         }
+    # ---- extras (rank 0 of a single-GPU run; each outside the timed regions above) ------------------------------------
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras_t0 = time.perf_counter()
+        has_ffps = any("f-fps" in l.methods for l in cfg.layers)
+        if has_ffps:       # the chain with the reference-identical F-FPS route: the cost of the deviation made visible
+            del run.chains[1:]
+            alt = ChainRunner(cfg, batch, dev, min(P, 3), rank, world, ffps="cdist")
+            ms_alt = alt.resident(10, 3)
+            line["value_ffps_reference_route"] = {"value": batch * 10 / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt / 10,
+                                                  "note": "F-FPS as torch.cdist (cuBLAS) + de6d_furthest_point_sampling_matrix: "
+                                                          "bit-identical indices to the reference pipeline on this GPU"}
+            del alt
+            torch.cuda.empty_cache()
+        line["reference_cuda"] = reference_cuda_leg(cfg, batch, dev, chain)
+        others = {}
+        for name in ("chain16", "stress131072"):
+            if name == args.config:
+                continue
+            a2 = argparse.Namespace(**vars(args))
+            a2.config, a2.batch = name, None
+            cfg2, b2 = config_of(a2)
+            try:
+                r2 = ChainRunner(cfg2, b2, dev, 3, rank, world)
+                ms2 = r2.resident(10, 3)
+                ms2_e2e = r2.e2e(10, ch.OpChain.SENSOR_KEYS)
+                r1 = ChainRunner(cfg2, b2, dev, 1, rank, world)
+                ms1 = r1.resident(10, 3)
+                k2, t2 = per_kernel_pass(cfg2, b2, dev, r2.hosts[0], reps=3)
+                others[name] = {"workload": workload_config(a2, b2, 1)["workload"], "frames_per_step": b2,
+                                "value": b2 * 10 / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / 10, "chains_in_flight": 3,
+                                "e2e_value": b2 * 10 / (ms2_e2e * 1e-3),
+                                "serial_value": b2 * 10 / (ms1 * 1e-3), "serial_ms_per_step": ms1 / 10,
+                                "kernels": [{kk: k[kk] for kk in ("entry", "shape", "ms_per_launch", "launches_per_step", "gbs", "frac_hbm")} for k in k2[:8]]}
+                del r2, r1
+            except Exception as e:  # noqa: BLE001
+                others[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+            torch.cuda.empty_cache()
+        line["other_configs"] = others
+        line["extras_seconds"] = round(time.perf_counter() - extras_t0, 1)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_seconds)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
         args.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -462,7 +625,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--config", default="chain64", choices=sorted(CONFIGS), help="BASELINE.json workload (default: configs[2])")
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (default: the config's)")
+    ap.add_argument("--no-extras", action="store_true", help="skip reference_cuda / other_configs / reference-route legs")
     ap.add_argument("--pipeline", type=int, default=6, help="independent chains in flight (1 = strictly serial steps)")
     ap.add_argument("--impl", default="de6d_b200", choices=["de6d_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -17,6 +17,13 @@
 namespace de6d {
 
 constexpr int GS_THREADS = 512;
+// tuning knobs (scripts/group_variants.py builds the library with other values and times them on the GPU)
+#ifndef DE6D_GS_U
+#define DE6D_GS_U 4        // index vectors in flight per thread
+#endif
+#ifndef DE6D_GS_MINB
+#define DE6D_GS_MINB 3     // CTAs per SM the register allocation must allow
+#endif
 
 // Leading coordinate rows of the fused grouper tail (de6d_group_concat): virtual rows 0..2 of the output are
 // xyz[idx] - new_xyz, rows 3.. are the feature channels.  A coordinate row is staged from the transposed cloud xyz_t
@@ -32,7 +39,7 @@ struct GroupXyz {
 // grid: (chunks, ceil(C/G), B).  Dynamic smem: G*n_pad floats + one mbarrier.  XYZ: the first 3 of the `c` rows are the
 // coordinate rows described above and `points` holds the remaining c - 3 channels (ns % 4 == 0 required).
 template <bool TMA, bool XYZ>
-__global__ void __launch_bounds__(GS_THREADS)
+__global__ void __launch_bounds__(GS_THREADS, DE6D_GS_MINB)
 group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chunk, const float *__restrict__ points,
                     const int *__restrict__ idx, float *__restrict__ out, long long out_bstride, GroupXyz gx) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -88,18 +95,31 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
     const int *ix = idx + (size_t)bs * ms;
     float *dst = out + (size_t)bs * out_bstride + (size_t)c0 * ms;
     const float *ctr = XYZ ? gx.new_xyz + (size_t)bs * gx.m * 3 : nullptr;
-    // chunk is a multiple of 4 and ms % 4 == 0 is checked by the host for this kernel
-    for (long long j = j0 + 4ll * threadIdx.x; j < j1; j += 4ll * GS_THREADS) {
-        const int4 k = ldg_stream_int4(ix + j);
-        const unsigned q = XYZ ? (unsigned)j / (unsigned)gx.ns : 0u;   // ms < 2^31 checked by the host; 4 slots share a centre
-        for (int g = 0; g < g_here; ++g) {
-            const float *r = rows + (size_t)g * n_pad;
-            float4 v = make_float4(r[k.x], r[k.y], r[k.z], r[k.w]);
-            if (XYZ) {   // branch-free: channel rows subtract +0.0f, which leaves every float (incl. -0, NaN payloads aside) as is
-                const float cv = (c0 + g < nx) ? __ldg(ctr + (size_t)q * 3 + (c0 + g)) : 0.f;
-                v.x = __fsub_rn(v.x, cv); v.y = __fsub_rn(v.y, cv); v.z = __fsub_rn(v.z, cv); v.w = __fsub_rn(v.w, cv);
+    // chunk is a multiple of 4 and ms % 4 == 0 is checked by the host for this kernel.  U index vectors are in flight per
+    // thread: with few rows per CTA (layer 1: one 64 KB row) the index stream is as large as the output stream and one
+    // 16-byte load per thread at a time cannot cover its latency (measured: 0.60 -> see profiles/r2 of the HBM peak).
+    constexpr int U = DE6D_GS_U;
+    constexpr long long STEP = 4ll * GS_THREADS;
+    for (long long j = j0 + 4ll * threadIdx.x; j < j1; j += U * STEP) {
+        int4 kk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j + u * STEP < j1) kk[u] = ldg_stream_int4(ix + j + u * STEP);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long ju = j + u * STEP;
+            if (ju >= j1) break;
+            const int4 k = kk[u];
+            const unsigned q = XYZ ? (unsigned)ju / (unsigned)gx.ns : 0u;   // ms < 2^31 checked by the host; 4 slots share a centre
+            for (int g = 0; g < g_here; ++g) {
+                const float *r = rows + (size_t)g * n_pad;
+                float4 v = make_float4(r[k.x], r[k.y], r[k.z], r[k.w]);
+                if (XYZ) {   // branch-free: channel rows subtract +0.0f, which leaves every float as it is
+                    const float cv = (c0 + g < nx) ? __ldg(ctr + (size_t)q * 3 + (c0 + g)) : 0.f;
+                    v.x = __fsub_rn(v.x, cv); v.y = __fsub_rn(v.y, cv); v.z = __fsub_rn(v.z, cv); v.w = __fsub_rn(v.w, cv);
+                }
+                stg_stream_float4(dst + (size_t)g * ms + ju, v);
             }
-            stg_stream_float4(dst + (size_t)g * ms + j, v);
         }
     }
 }

@@ -271,3 +271,46 @@ def test_nms_and_class_agnostic_nms(pair, nms_type):
             _same(sa, sb, "class_agnostic_nms selected"); _same(va, vb, "class_agnostic_nms scores")
             checked += 1
     assert checked >= 12
+
+
+def test_whole_op_chain_equals_reference_kernels_chain(pair):
+    """The benchmarked op chain (de6d_b200.chain.OpChain, CUDA graph, fused grouping, shared ball-query grids) with the
+    F-FPS route of an unmodified checkout (torch.cdist + matrix kernel) against the same chain issued op by op with the
+    reference's own kernels through the reference's own python (oracle/chain_ref_cuda.py): every sampled index, count,
+    grouped tensor and NMS selection bit-identical.  With the fused F-FPS route everything not downstream of the F-FPS
+    picks is still identical and the F-FPS picks themselves agree as tests/test_parity_gpu.py pins."""
+    from de6d_b200 import chain as ch
+    from oracle import chain_ref_cuda
+    _, theirs = pair
+    cfg = ch.ChainConfig(
+        n_points=4096,
+        layers=[ch.SALayer((1024,), ('d-fps',), ((0, 4096),), (0.4, 0.8, 1.6), (16, 16, 32), 1),
+                ch.SALayer((256, 256), ('f-fps', 'd-fps'), ((0, 1024), (0, 1024)), (0.8, 1.6), (16, 32), 32),
+                ch.SALayer((128, 128), ('s-fps', 'd-fps'), ((0, 256), (256, 512)), (1.6, 4.8), (16, 32), 64)],
+        n_votes=128, vote_radii=(4.8, 6.4), vote_nsamples=(16, 32), vote_c_in=64, n_proposals=256, nms_thresh=0.1)
+    B = 4
+    host = ch.make_inputs(cfg, B, seed=11)
+    oc = ch.OpChain(cfg, B, use_graph=True, ffps="cdist")
+    oc.step_host(host)
+    torch.cuda.synchronize()
+    ref, _ = chain_ref_cuda.run(cfg, oc.inputs, theirs, keep_groups=True)
+    torch.cuda.synchronize()
+    n_cmp = 0
+    for k, v in ref.items():
+        if k == "nms_keep_list":
+            for f, sel in enumerate(v):
+                n = int(oc.outputs["nms_num"][f])
+                assert n == sel.numel(), "frame %d keeps %d vs %d" % (f, n, sel.numel())
+                _same(oc.outputs["nms_keep"][f, :n], sel, "nms keep frame %d" % f)
+        else:
+            _same(oc.outputs[k], v, k)
+        n_cmp += 1
+    assert n_cmp >= 20
+    fused = ch.OpChain(cfg, B, use_graph=False, ffps="fused")
+    fused.step_host(host)
+    torch.cuda.synchronize()
+    _same(fused.outputs["l0_idx"], ref["l0_idx"], "layer-0 D-FPS")
+    _same(fused.outputs["l1_idx"][:, 256:], ref["l1_idx"][:, 256:], "layer-1 D-FPS half")
+    a, b = fused.outputs["l1_idx"][:, :256].cpu().numpy(), ref["l1_idx"][:, :256].cpu().numpy()
+    overlap = np.mean([len(set(a[i]) & set(b[i])) / 256.0 for i in range(B)])
+    assert overlap >= 0.98, overlap

@@ -919,7 +919,7 @@ def test_chain_graph_equals_eager_and_shards_concatenate(lib):
     comp.step_host(host)
     torch.cuda.synchronize()
     for k, v in eager.outputs.items():
-        if isinstance(v, torch.Tensor):
+        if isinstance(v, torch.Tensor) and not k.endswith("_xyz_t"):     # the transposed clouds exist only on the fused route
             assert torch.equal(v, comp.outputs[k]), k
     # batch sharding: two half-batches reproduce the full batch bit for bit (ops never mix frames)
     halves = []
