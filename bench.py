@@ -240,7 +240,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.batch, max(args.gpus, 1),
+        "config": workload_config(args, config_of(args)[1], max(args.gpus, 1),
                                   note="CPU arm: each step is a bounded sample of %d frames of this workload" % per_step),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d frames per step, one oracle process per host core (%d), %d steps" % (per_step, cores, args.steps)},

@@ -19,11 +19,12 @@ namespace de6d {
 constexpr int GS_THREADS = 512;
 // tuning knobs (scripts/group_variants.py builds the library with other values and times them on the GPU)
 #ifndef DE6D_GS_U
-#define DE6D_GS_U 4        // index vectors in flight per thread
+#define DE6D_GS_U 2        // index vectors in flight per thread (r2 A/B on B200: 2 with 3 CTAs/SM is best or within 1 %)
 #endif
 #ifndef DE6D_GS_MINB
-#define DE6D_GS_MINB 3     // CTAs per SM the register allocation must allow
+#define DE6D_GS_MINB 3     // CTAs per SM the register allocation must allow (512-thread CTAs with <= 64 KB of rows)
 #endif
+constexpr int GS_THREADS_BIG = 1024;   // one CTA per SM holding > 64 KB of rows (large clouds, few channels)
 
 // Leading coordinate rows of the fused grouper tail (de6d_group_concat): virtual rows 0..2 of the output are
 // xyz[idx] - new_xyz, rows 3.. are the feature channels.  A coordinate row is staged from the transposed cloud xyz_t
@@ -38,8 +39,8 @@ struct GroupXyz {
 
 // grid: (chunks, ceil(C/G), B).  Dynamic smem: G*n_pad floats + one mbarrier.  XYZ: the first 3 of the `c` rows are the
 // coordinate rows described above and `points` holds the remaining c - 3 channels (ns % 4 == 0 required).
-template <bool TMA, bool XYZ>
-__global__ void __launch_bounds__(GS_THREADS, DE6D_GS_MINB)
+template <bool TMA, bool XYZ, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chunk, const float *__restrict__ points,
                     const int *__restrict__ idx, float *__restrict__ out, long long out_bstride, GroupXyz gx) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -81,10 +82,10 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
         plain = true;
         float *dstrow = rows + (size_t)g * n_pad;
         if (src) {
-            for (int i = threadIdx.x; i < n; i += GS_THREADS) dstrow[i] = src[i];
+            for (int i = threadIdx.x; i < n; i += THREADS) dstrow[i] = src[i];
         } else {
             const float *a = gx.xyz + (size_t)bs * n * 3 + (c0 + g);
-            for (int i = threadIdx.x; i < n; i += GS_THREADS) dstrow[i] = __ldg(a + (size_t)i * 3);
+            for (int i = threadIdx.x; i < n; i += THREADS) dstrow[i] = __ldg(a + (size_t)i * 3);
         }
     }
     if (plain || !TMA) __syncthreads();   // `plain` is uniform over the CTA
@@ -98,8 +99,8 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
     // chunk is a multiple of 4 and ms % 4 == 0 is checked by the host for this kernel.  U index vectors are in flight per
     // thread: with few rows per CTA (layer 1: one 64 KB row) the index stream is as large as the output stream and one
     // 16-byte load per thread at a time cannot cover its latency (measured: 0.60 -> see profiles/r2 of the HBM peak).
-    constexpr int U = DE6D_GS_U;
-    constexpr long long STEP = 4ll * GS_THREADS;
+    constexpr int U = (THREADS == GS_THREADS_BIG) ? 4 : DE6D_GS_U;
+    constexpr long long STEP = 4ll * THREADS;
     for (long long j = j0 + 4ll * threadIdx.x; j < j1; j += U * STEP) {
         int4 kk[U];
 #pragma unroll
@@ -240,11 +241,21 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
     // channel rows per CTA: as many as fit in ~64 KB (three CTAs per SM hide the index-load latency better than one
     // CTA with 192 KB: measured +3..10 % on B200, scripts/group_tune.py), at most 8, at least one if a row fits at all
     int G = (int)(smem_budget / ((size_t)n_pad * 4 + 1));
+    const int Gmax = G;
     const int G64 = (int)((64 * 1024) / ((size_t)n_pad * 4 + 1));
     if (G > 1 && G64 >= 1 && G > G64) G = G64;
     if (G > 1 && G64 < 1) G = 1;
     if (G > c) G = c;
     if (G > 8) G = 8;
+    // Large clouds with few channels (layer 1: 16384 points, 3 + 1 rows of 64 KB): with one row per CTA every CTA re-reads
+    // its whole index chunk for a single output row, so the SM's read traffic (row + indices) is 1.5x its write traffic
+    // and the kernel stops at ~0.6 of the HBM peak (r2 measurement).  Two or three rows per CTA (one 1024-thread CTA per
+    // SM, up to 200 KB of rows) halve the index re-reads.
+    const bool big = (G64 < 2) && Gmax >= 2 && c >= 2;
+    if (big) {
+        const int groups = ceil_div(c, Gmax);
+        G = ceil_div(c, groups);
+    }
     bool staged = aligned && G >= 1 && ms >= 2ll * n;
     if (gx) {
         if (!(staged && gx->ns % 4 == 0 && ms < (1ll << 31))) return DE6D_OK;   // not launched: caller falls back
@@ -256,28 +267,52 @@ static int group_forward(int b, int c, int n, long long ms, const float *points,
 
     if (staged) {
         const int cgroups = ceil_div(c, G);
-        // enough CTAs to fill the machine, but each CTA should write >= ~2x what it stages
-        long long min_chunk = (long long)n * 2;
-        if (min_chunk < 4096) min_chunk = 4096;
-        long long want = ceil_div_ll(8 * 148, (long long)b * cgroups);   // ~8 waves of CTAs: small tail
-        long long chunks = want < 1 ? 1 : want;
-        long long chunk = ceil_div_ll(ms, chunks);
-        if (chunk < min_chunk) chunk = min_chunk;
-        chunk = (chunk + 3) & ~3ll;
-        chunks = ceil_div_ll(ms, chunk);
+        long long chunk, chunks;
+        if (big) {
+            // chunks per row group: minimise waves x per-CTA traffic, traffic = max(reads, writes) of one CTA
+            const long long slots = 148;
+            double best = 1e300;
+            chunks = 1;
+            for (long long k = 1; k <= 16; ++k) {
+                long long ch = (ceil_div_ll(ms, k) + 3) & ~3ll;
+                if (k > 1 && ch < (long long)n) break;              // never stage more than is written per row
+                const long long ctas = (long long)b * cgroups * ceil_div_ll(ms, ch);
+                const double reads = (double)G * n * 4 + (double)ch * 4, writes = (double)G * ch * 4;
+                const double t = (double)ceil_div_ll(ctas, slots) * (reads > writes ? reads : writes);
+                if (t < best * 0.999) { best = t; chunks = k; }
+            }
+            chunk = (ceil_div_ll(ms, chunks) + 3) & ~3ll;
+            chunks = ceil_div_ll(ms, chunk);
+        } else {
+            // enough CTAs to fill the machine, but each CTA should write >= ~2x what it stages
+            long long min_chunk = (long long)n * 2;
+            if (min_chunk < 4096) min_chunk = 4096;
+            long long want = ceil_div_ll(8 * 148, (long long)b * cgroups);   // ~8 waves of CTAs: small tail
+            chunks = want < 1 ? 1 : want;
+            chunk = ceil_div_ll(ms, chunks);
+            if (chunk < min_chunk) chunk = min_chunk;
+            chunk = (chunk + 3) & ~3ll;
+            chunks = ceil_div_ll(ms, chunk);
+        }
         size_t smem = 128 + (size_t)G * n_pad * 4;
-        static unsigned long long devs[4] = {0, 0, 0, 0};
+        static unsigned long long devs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         dim3 grid((unsigned)chunks, cgroups, b);
         const GroupXyz none = {nullptr, nullptr, nullptr, 4, 0};
-#define DE6D_GROUP_LAUNCH(T, X, slot)                                                                                          \
+#define DE6D_GROUP_LAUNCH(T, X, TH, MB, slot)                                                                                   \
     do {                                                                                                                       \
         if (smem > 48 * 1024)                                                                                                  \
-            if (int rc = de6d_ensure_smem(group_staged_kernel<T, X>, 208 * 1024, devs[slot], "group smem attribute")) return rc; \
-        group_staged_kernel<T, X><<<grid, GS_THREADS, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride,     \
+            if (int rc = de6d_ensure_smem(group_staged_kernel<T, X, TH, MB>, 208 * 1024, devs[slot], "group smem attribute")) return rc; \
+        group_staged_kernel<T, X, TH, MB><<<grid, TH, smem, s>>>(c, n, ms, G, n_pad, chunk, points, idx, out, out_bstride,     \
                                                                   gx ? *gx : none);                                            \
     } while (0)
-        if (gx) { if (tma_ok) DE6D_GROUP_LAUNCH(true, true, 3); else DE6D_GROUP_LAUNCH(false, true, 2); }
-        else { if (tma_ok) DE6D_GROUP_LAUNCH(true, false, 1); else DE6D_GROUP_LAUNCH(false, false, 0); }
+#define DE6D_GROUP_PICK(TH, MB, base)                                                                     \
+    do {                                                                                                  \
+        if (gx) { if (tma_ok) DE6D_GROUP_LAUNCH(true, true, TH, MB, base + 3); else DE6D_GROUP_LAUNCH(false, true, TH, MB, base + 2); } \
+        else { if (tma_ok) DE6D_GROUP_LAUNCH(true, false, TH, MB, base + 1); else DE6D_GROUP_LAUNCH(false, false, TH, MB, base + 0); }  \
+    } while (0)
+        if (big) DE6D_GROUP_PICK(GS_THREADS_BIG, 1, 4);
+        else DE6D_GROUP_PICK(GS_THREADS, DE6D_GS_MINB, 0);
+#undef DE6D_GROUP_PICK
 #undef DE6D_GROUP_LAUNCH
         DE6D_CHECK_LAUNCH("group_staged_kernel");
         if (launched) *launched = true;

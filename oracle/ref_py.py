@@ -16,6 +16,7 @@ experimental samplers).
 import importlib
 import os
 import sys
+import tempfile
 import types
 from types import SimpleNamespace
 
@@ -46,6 +47,15 @@ def load_tree(root="pcdet", extensions=None):
             importlib.import_module("SharedArray")
         except ImportError:
             sys.modules["SharedArray"] = types.ModuleType("SharedArray")
+    # pointnet2_stack/pointnet2_utils.py jits helpers with numba cache=True; the cache index is keyed by file path but the
+    # pickles name the importing module, so a tree loaded under a second root must not see the first root's cache
+    cache_dir = os.path.join(tempfile.gettempdir(), "de6d_numba_cache_%s_%d" % (root, os.getuid()))
+    os.environ["NUMBA_CACHE_DIR"] = cache_dir
+    try:
+        import numba
+        numba.config.CACHE_DIR = cache_dir
+    except Exception:
+        pass
     for sub in _PACKAGES:
         name = root + ("." + sub if sub else "")
         if name not in sys.modules or not hasattr(sys.modules[name], "__path__"):
