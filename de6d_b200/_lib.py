@@ -46,6 +46,7 @@ PROTOTYPES = {
     "de6d_boxes_overlap_bev": [_i, _p, _i, _p, _p, _p],
     "de6d_boxes_iou_bev": [_i, _p, _i, _p, _p, _p],
     "de6d_boxes_iou3d": [_i, _p, _i, _p, _p, _p],
+    "de6d_boxes_iou3d9": [_i, _p, _i, _p, _p, _p],
     "de6d_nms_workspace_bytes": [_i, _i],
     "de6d_nms_workspace_init": [_i, _p, _p],
     "de6d_nms_batched": [_i, _i, _p, _p, _f, _i, _p, _p, _p, _sz, _p],

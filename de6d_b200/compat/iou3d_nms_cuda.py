@@ -33,6 +33,18 @@ def boxes_iou3d_gpu(boxes_a, boxes_b, ans_iou):
     return 1
 
 
+def boxes_iou3d9_gpu(boxes_a, boxes_b, ans_iou):
+    """Extension of this package: full-pose IoU of (N, 9) x (M, 9) boxes [x, y, z, dx, dy, dz, rz, ry, rx]."""
+    for t, name in ((boxes_a, "boxes_a"), (boxes_b, "boxes_b")):
+        if t.dim() != 2 or t.size(1) != 9:
+            raise ValueError("%s must have shape (N, 9)" % name)
+    if ans_iou.numel() < boxes_a.size(0) * boxes_b.size(0):
+        raise ValueError("ans_iou is too small")
+    call("de6d_boxes_iou3d9", boxes_a.size(0), dev(boxes_a, "boxes_a", f32), boxes_b.size(0), dev(boxes_b, "boxes_b", f32),
+         dev(ans_iou, "ans_iou", f32), stream_ptr())
+    return 1
+
+
 def boxes_iou_bev_cpu(boxes_a, boxes_b, ans_iou):
     """Host tensors in, host tensor out, evaluated on the calling host thread like the reference
     (iou3d_cpu.cpp:232-252) -- its callers run in forked DataLoader workers (database_sampler.py:232-233) where no CUDA
@@ -54,9 +66,12 @@ def boxes_iou_bev_cpu(boxes_a, boxes_b, ans_iou):
     return 1
 
 
-def _nms(boxes, keep, thresh, normal):
+def _nms(boxes, keep, thresh, mode):
     n = boxes.size(0)
-    ptr = _boxes(boxes, "boxes")
+    width = 9 if mode == 2 else 7
+    if boxes.dim() != 2 or boxes.size(1) != width:
+        raise ValueError("boxes must have shape (N, %d)" % width)
+    ptr = dev(boxes, "boxes", f32)
     if keep.is_cuda or keep.dtype != torch.int64 or not keep.is_contiguous():
         raise ValueError("keep must be a contiguous CPU LongTensor (reference contract, iou3d_nms_utils.py:97)")
     if keep.numel() < n:
@@ -70,11 +85,16 @@ def _nms(boxes, keep, thresh, normal):
     call("de6d_nms_workspace_init", 1, ws.data_ptr(), s)
     keep_dev = torch.empty(n, dtype=torch.int64, device=boxes.device)
     num = torch.zeros(1, dtype=torch.int32, device=boxes.device)
-    call("de6d_nms_batched", 1, n, ptr, None, float(thresh), int(normal), keep_dev.data_ptr(), num.data_ptr(),
+    call("de6d_nms_batched", 1, n, ptr, None, float(thresh), int(mode), keep_dev.data_ptr(), num.data_ptr(),
          ws.data_ptr(), ws_bytes, s)
     num_out = int(num.item())  # the reference API returns a host int: this sync is part of its contract
     keep[:num_out].copy_(keep_dev[:num_out])
     return num_out
+
+
+def nms9_gpu(boxes, keep, nms_overlap_thresh):
+    """Extension of this package: nms_gpu's contract with the full-pose IoU on (N, 9) boxes."""
+    return _nms(boxes, keep, nms_overlap_thresh, 2)
 
 
 def nms_gpu(boxes, keep, nms_overlap_thresh):

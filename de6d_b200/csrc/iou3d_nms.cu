@@ -17,7 +17,9 @@
 //     the suppression words stay on the device, and the LAST tile-CTA of each frame (atomic ticket) runs the
 //     greedy sweep out of shared memory -- one launch for a whole batch of frames, no host synchronisation.
 #include "common.cuh"
+#include "box9.cuh"
 #include <math.h>
+#include <type_traits>
 
 namespace de6d {
 
@@ -220,13 +222,18 @@ iou_matrix_kernel(int na, const float *__restrict__ boxes_a, int nb, const float
 // ---------------------------------------------------------------------------------------------------------
 constexpr int NMS_T = 256;
 
-template <bool NORMAL>
+// MODE 0: rotated BEV IoU (nms_gpu), 1: axis-aligned BEV IoU (nms_normal_gpu), boxes (F, N, 7);
+// MODE 2: full-pose 3-D IoU (box9.cuh), boxes (F, N, 9) -- the pitch / roll aware NMS Det6D's 9-DoF predictions call for.
+template <int MODE>
 __global__ void __launch_bounds__(NMS_T)
 nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ nvalid, float thresh,
            unsigned long long *__restrict__ mask_all, unsigned int *__restrict__ tickets, long long *__restrict__ keep_all,
            int *__restrict__ num_keep, int sweep_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ BoxGeo grow[64], gcol[64];
+    constexpr bool NORMAL = MODE == 1;
+    constexpr int BS = MODE == 2 ? 9 : 7;                      // floats per box
+    using Geo = typename std::conditional<MODE == 2, Box9Geo, BoxGeo>::type;
+    __shared__ Geo grow[64], gcol[64];
     __shared__ unsigned int s_last;
     __shared__ unsigned long long s_diag[64];
     __shared__ unsigned long long s_keepbits;
@@ -237,7 +244,7 @@ nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ n
     const int f = blockIdx.y;
     const int cb = ceil_div(n, 64);
     const int nv = nvalid ? min(max(nvalid[f], 0), n) : n;
-    const float *boxes = boxes_all + (size_t)f * n * 7;
+    const float *boxes = boxes_all + (size_t)f * n * BS;
     unsigned long long *mask = mask_all + (size_t)f * n * cb;
     const int tid = threadIdx.x;
 
@@ -251,7 +258,10 @@ nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ n
             const bool isc = tid >= 64;
             const int i = isc ? tid - 64 : tid;
             const int gi = (isc ? ct : rt) * 64 + i;
-            if (gi < nv) (isc ? gcol : grow)[i] = make_geo(boxes + (size_t)gi * 7);
+            if (gi < nv) {
+                if constexpr (MODE == 2) (isc ? gcol : grow)[i] = make_geo9(boxes + (size_t)gi * 9);
+                else (isc ? gcol : grow)[i] = make_geo(boxes + (size_t)gi * 7);
+            }
         }
         __syncthreads();
         const int r = tid >> 2, part = tid & 3;  // row r, columns part*16 .. +15
@@ -284,7 +294,10 @@ nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ n
                 for (int jj = 0; jj < 16; ++jj) {
                     const int j = part * 16 + jj, gj = ct * 64 + j;
                     if (j < jstart || gj >= nv) continue;
-                    if (!cannot_touch(grow[r], gcol[j])) cand |= 1u << jj;
+                    bool far;
+                    if constexpr (MODE == 2) far = cannot_touch9(grow[r], gcol[j]);
+                    else far = cannot_touch(grow[r], gcol[j]);
+                    if (!far) cand |= 1u << jj;
                 }
                 if (cand) {
                     int at = atomicAdd(&s_qn, __popc(cand));
@@ -299,7 +312,9 @@ nms_kernel(int n, const float *__restrict__ boxes_all, const int *__restrict__ n
             const int qn = s_qn;
             for (int q = tid; q < qn; q += NMS_T) {
                 const int code = s_queue[q], qr = code >> 6, qj = code & 63;
-                const float v = iou_from_overlap(overlap_area(grow[qr], gcol[qj]), grow[qr].area, gcol[qj].area);
+                float v;
+                if constexpr (MODE == 2) v = iou9(grow[qr], gcol[qj]);
+                else v = iou_from_overlap(overlap_area(grow[qr], gcol[qj]), grow[qr].area, gcol[qj].area);
                 if (v > thresh) atomicOr(&s_words[qr], 1ull << qj);
             }
             __syncthreads();
@@ -401,6 +416,51 @@ extern "C" int de6d_boxes_iou3d(int na, const float *boxes_a, int nb, const floa
     return iou_matrix_launch(2, na, boxes_a, nb, boxes_b, ans_iou, stream);
 }
 
+// Full-pose IoU matrix: boxes_a (na, 9) x boxes_b (nb, 9) -> (na, nb).  32 x 32 tiles: bounding-sphere reject, then the
+// surviving pairs are queued in shared memory and clipped densely (the clip is ~5000 instructions and ~2 KB of local
+// memory per thread: evaluated in place it would leave most lanes of a warp waiting on a few surviving pairs).
+namespace de6d {
+__global__ void __launch_bounds__(256)
+iou9_matrix_kernel(int na, const float *__restrict__ a, int nb, const float *__restrict__ b, float *__restrict__ out) {
+    __shared__ Box9Geo ga[32], gb[32];
+    __shared__ unsigned short s_queue[32 * 32];
+    __shared__ int s_qn;
+    const int tid = threadIdx.x;
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    if (tid < 32) { if (a0 + tid < na) ga[tid] = make_geo9(a + (size_t)(a0 + tid) * 9); }
+    else if (tid < 64) { if (b0 + tid - 32 < nb) gb[tid - 32] = make_geo9(b + (size_t)(b0 + tid - 32) * 9); }
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
+    const int j = tid & 31, bj = b0 + j;
+    if (bj < nb) {
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            const int i = (tid >> 5) + 8 * r, ai = a0 + i;
+            if (ai >= na) break;
+            if (cannot_touch9(ga[i], gb[j])) out[(size_t)ai * nb + bj] = 0.f;
+            else s_queue[atomicAdd(&s_qn, 1)] = (unsigned short)(i * 32 + j);
+        }
+    }
+    __syncthreads();
+    const int qn = s_qn;
+    for (int q = tid; q < qn; q += 256) {
+        const int code = s_queue[q], i = code >> 5, jq = code & 31;
+        out[(size_t)(a0 + i) * nb + b0 + jq] = iou9(ga[i], gb[jq]);
+    }
+}
+}  // namespace de6d
+
+extern "C" int de6d_boxes_iou3d9(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, cudaStream_t stream) {
+    if (na < 0 || nb < 0) return de6d_set_error(DE6D_ERR_INVALID, "boxes_iou3d9: negative size");
+    if (na == 0 || nb == 0) return DE6D_OK;
+    if (!boxes_a || !boxes_b || !ans_iou) return de6d_set_error(DE6D_ERR_INVALID, "boxes_iou3d9: null pointer");
+    dim3 grid(de6d::ceil_div(nb, 32), de6d::ceil_div(na, 32));
+    if (grid.y > 65535) return de6d_set_error(DE6D_ERR_INVALID, "boxes_iou3d9: too many boxes");
+    de6d::iou9_matrix_kernel<<<grid, 256, 0, stream>>>(na, boxes_a, nb, boxes_b, ans_iou);
+    DE6D_CHECK_LAUNCH("iou9_matrix_kernel");
+    return DE6D_OK;
+}
+
 extern "C" size_t de6d_nms_workspace_bytes(int frames, int n) {
     if (frames <= 0 || n <= 0) return 256;
     size_t cb = (size_t)(n + 63) / 64;
@@ -420,7 +480,7 @@ extern "C" int de6d_nms_workspace_init(int frames, void *workspace, cudaStream_t
     return DE6D_OK;
 }
 
-extern "C" int de6d_nms_batched(int frames, int n, const float *boxes, const int *nvalid, float thresh, int normal,
+extern "C" int de6d_nms_batched(int frames, int n, const float *boxes, const int *nvalid, float thresh, int mode,
                                 long long *keep, int *num_keep, void *workspace, size_t workspace_bytes,
                                 cudaStream_t stream) {
     if (frames < 0 || n < 0) return de6d_set_error(DE6D_ERR_INVALID, "nms: negative size");
@@ -444,15 +504,18 @@ extern "C" int de6d_nms_batched(int frames, int n, const float *boxes, const int
     int in_smem = smem_full <= 160 * 1024;
     size_t smem = in_smem ? smem_full : (size_t)cb * 8;
     if (smem > 200 * 1024) return de6d_set_error(DE6D_ERR_INVALID, "nms: too many boxes for the sweep");
-    static unsigned long long devs[2] = {0, 0};
+    static unsigned long long devs[3] = {0, 0, 0};
+    if (mode < 0 || mode > 2) return de6d_set_error(DE6D_ERR_INVALID, "nms: unknown mode");
     {
-        int rc = normal ? de6d_ensure_smem(nms_kernel<true>, 200 * 1024, devs[1], "nms smem attribute")
-                        : de6d_ensure_smem(nms_kernel<false>, 200 * 1024, devs[0], "nms smem attribute");
+        int rc = mode == 1 ? de6d_ensure_smem(nms_kernel<1>, 200 * 1024, devs[1], "nms smem attribute")
+                 : mode == 2 ? de6d_ensure_smem(nms_kernel<2>, 200 * 1024, devs[2], "nms smem attribute")
+                             : de6d_ensure_smem(nms_kernel<0>, 200 * 1024, devs[0], "nms smem attribute");
         if (rc) return rc;
     }
     dim3 grid((unsigned)tiles, frames);
-    if (normal) nms_kernel<true><<<grid, NMS_T, smem, stream>>>(n, boxes, nvalid, thresh, mask, tickets, keep, num_keep, in_smem);
-    else nms_kernel<false><<<grid, NMS_T, smem, stream>>>(n, boxes, nvalid, thresh, mask, tickets, keep, num_keep, in_smem);
+    if (mode == 1) nms_kernel<1><<<grid, NMS_T, smem, stream>>>(n, boxes, nvalid, thresh, mask, tickets, keep, num_keep, in_smem);
+    else if (mode == 2) nms_kernel<2><<<grid, NMS_T, smem, stream>>>(n, boxes, nvalid, thresh, mask, tickets, keep, num_keep, in_smem);
+    else nms_kernel<0><<<grid, NMS_T, smem, stream>>>(n, boxes, nvalid, thresh, mask, tickets, keep, num_keep, in_smem);
     DE6D_CHECK_LAUNCH("nms_kernel");
     return DE6D_OK;
 }

@@ -44,6 +44,29 @@ def boxes_iou3d_gpu(boxes_a, boxes_b):
     return ans
 
 
+def boxes_iou3d_9dof_gpu(boxes_a, boxes_b):
+    """Full-pose IoU (not in the reference, whose boxes_iou3d_gpu ignores pitch and roll): boxes (N, 9) / (M, 9)
+    [x, y, z, dx, dy, dz, rz, ry, rx], rotation as box_utils.boxes3d_to_corners_3d (pcdet/utils/box_utils.py:59-72) -> (N, M).
+    For ry = rx = 0 it is the exact-geometry value of what boxes_iou3d_gpu approximates (the reference's BEV clipping
+    pads its corner tests by 1e-2 m, so the two agree to ~1e-3)."""
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 9
+    ans = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=torch.float32, device=boxes_a.device)
+    _ext.boxes_iou3d9_gpu(boxes_a.contiguous(), boxes_b.contiguous(), ans)
+    return ans
+
+
+def nms_gpu_9dof(boxes, scores, thresh, pre_maxsize=None, **kwargs):
+    """nms_gpu (reference :84-99) on (N, 9) boxes with the full-pose 3-D IoU: returns (kept indices, None)."""
+    assert boxes.shape[1] == 9
+    order = scores.sort(0, descending=True)[1]
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    boxes = boxes[order].contiguous()
+    keep = torch.empty(boxes.size(0), dtype=torch.int64)
+    num_out = _ext.nms9_gpu(boxes, keep, thresh)
+    return order[keep[:num_out].to(boxes.device)].contiguous(), None
+
+
 def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
     """(reference :84-99) returns (indices into `boxes` of the kept boxes in descending score order, None)."""
     assert boxes.shape[1] == 7
@@ -75,8 +98,8 @@ class BatchedNMS:
         keep, num = nms(boxes, scores, thresh)           # keep (F, n) int64 indices into boxes[f], num (F) int32
     """
 
-    def __init__(self, frames, n, device="cuda"):
-        self.frames, self.n = frames, n
+    def __init__(self, frames, n, device="cuda", box_dim=7):
+        self.frames, self.n, self.box_dim = frames, n, box_dim      # box_dim 9: full-pose IoU (nms_gpu_9dof)
         lib = load()
         self.ws_bytes = int(lib.de6d_nms_workspace_bytes(frames, n))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
@@ -86,12 +109,14 @@ class BatchedNMS:
 
     def __call__(self, boxes, scores, thresh, nvalid=None, normal=False, presorted=False):
         F, n = self.frames, self.n
-        assert boxes.shape == (F, n, 7) and boxes.dtype == torch.float32
+        D = self.box_dim
+        assert boxes.shape == (F, n, D) and boxes.dtype == torch.float32
+        assert not (normal and D == 9), "the axis-aligned variant takes 7-value boxes"
         if presorted:
             order, sorted_boxes = None, boxes.contiguous()
         else:
             order = scores.sort(1, descending=True)[1]
-            sorted_boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, 7)).contiguous()
+            sorted_boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, D)).contiguous()
         if nvalid is not None:
             if not (nvalid.is_cuda and nvalid.dtype == torch.int32 and nvalid.is_contiguous() and nvalid.numel() == F
                     and nvalid.device == boxes.device):
@@ -99,7 +124,7 @@ class BatchedNMS:
         if not boxes.is_cuda or boxes.device != self.ws.device:
             raise ValueError("boxes must live on %s" % self.ws.device)
         call("de6d_nms_batched", F, n, sorted_boxes.data_ptr(), None if nvalid is None else nvalid.data_ptr(),
-             float(thresh), int(bool(normal)), self.keep_pos.data_ptr(), self.num.data_ptr(), self.ws.data_ptr(),
+             float(thresh), 2 if D == 9 else int(bool(normal)), self.keep_pos.data_ptr(), self.num.data_ptr(), self.ws.data_ptr(),
              self.ws_bytes, torch.cuda.current_stream().cuda_stream)
         if order is None:
             return self.keep_pos, self.num
@@ -110,6 +135,6 @@ class BatchedNMS:
 
 def nms_gpu_batched(boxes, scores, thresh, nvalid=None, normal=False):
     """Functional form of BatchedNMS for one-off calls: boxes (F, n, 7), scores (F, n)."""
-    op = BatchedNMS(boxes.shape[0], boxes.shape[1], device=boxes.device)
+    op = BatchedNMS(boxes.shape[0], boxes.shape[1], device=boxes.device, box_dim=boxes.shape[2])
     keep, num = op(boxes, scores, thresh, nvalid=nvalid, normal=normal)
     return keep.clone(), num.clone()

@@ -29,8 +29,12 @@ def class_agnostic_nms(box_scores, box_preds, nms_config, score_thresh=None):
     if box_scores.shape[0] > 0:
         box_scores_nms, indices = torch.topk(box_scores, k=min(_cfg(nms_config, "NMS_PRE_MAXSIZE"), box_scores.shape[0]))
         boxes_for_nms = box_preds[indices]
-        keep_idx, _ = getattr(iou3d_nms_utils, _cfg(nms_config, "NMS_TYPE", "nms_gpu"))(
-            boxes_for_nms[:, 0:7], box_scores_nms, _cfg(nms_config, "NMS_THRESH"))
+        nms_type = _cfg(nms_config, "NMS_TYPE", "nms_gpu")
+        # NMS_TYPE "nms_gpu_9dof" (not in the reference) keeps rz, ry, rx: the reference slices [:, 0:7] (:18) and so
+        # suppresses with the yaw-only BEV IoU even though Det6D's boxes carry pitch and roll
+        width = 9 if nms_type == "nms_gpu_9dof" else 7
+        keep_idx, _ = getattr(iou3d_nms_utils, nms_type)(
+            boxes_for_nms[:, 0:width], box_scores_nms, _cfg(nms_config, "NMS_THRESH"))
         selected = indices[keep_idx[:_cfg(nms_config, "NMS_POST_MAXSIZE")]]
     if score_thresh is not None:
         original_idxs = scores_mask.nonzero().view(-1)
@@ -51,7 +55,8 @@ class BatchedClassAgnosticNMS:
         self.post = min(int(_cfg(nms_config, "NMS_POST_MAXSIZE")), self.pre)
         self.thresh = float(_cfg(nms_config, "NMS_THRESH"))
         self.normal = _cfg(nms_config, "NMS_TYPE", "nms_gpu") == "nms_normal_gpu"
-        self.nms = iou3d_nms_utils.BatchedNMS(frames, self.pre, device=device)
+        self.width = 9 if _cfg(nms_config, "NMS_TYPE", "nms_gpu") == "nms_gpu_9dof" else 7
+        self.nms = iou3d_nms_utils.BatchedNMS(frames, self.pre, device=device, box_dim=self.width)
 
     @torch.no_grad()
     def __call__(self, box_scores, box_preds, score_thresh=None):
@@ -66,7 +71,7 @@ class BatchedClassAgnosticNMS:
             nvalid = torch.full((F,), self.pre, dtype=torch.int32, device=scores.device)
         top_scores, order = torch.sort(scores, dim=1, descending=True)
         order, top_scores = order[:, :self.pre], top_scores[:, :self.pre]
-        boxes = torch.gather(box_preds[..., 0:7], 1, order.unsqueeze(-1).expand(-1, -1, 7)).contiguous()
+        boxes = torch.gather(box_preds[..., 0:self.width], 1, order.unsqueeze(-1).expand(-1, -1, self.width)).contiguous()
         keep_pos, num = self.nms(boxes, None, self.thresh, nvalid=nvalid.contiguous(), normal=self.normal, presorted=True)
         keep_pos = keep_pos[:, :self.post]
         num = num.clamp(max=self.post)

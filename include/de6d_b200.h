@@ -198,8 +198,16 @@ int de6d_boxes_iou3d(int na, const float *boxes_a, int nb, const float *boxes_b,
  * nms_gpu(boxes, keep HOST int64, thresh) -> num_to_keep is this call with frames = 1 plus a D2H copy. */
 size_t de6d_nms_workspace_bytes(int frames, int n);
 int de6d_nms_workspace_init(int frames, void *workspace, cudaStream_t stream);
-int de6d_nms_batched(int frames, int n, const float *boxes, const int *nvalid, float thresh, int normal,
+int de6d_nms_batched(int frames, int n, const float *boxes, const int *nvalid, float thresh, int mode,
                      long long *keep, int *num_keep, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+/* mode: 0 = rotated BEV IoU (nms_gpu), 1 = axis-aligned BEV IoU (nms_normal_gpu), boxes (frames, n, 7);
+ *       2 = full-pose 3-D IoU, boxes (frames, n, 9) [x, y, z, dx, dy, dz, rz, ry, rx] (see de6d_boxes_iou3d9). */
+
+/* Full-pose (9-DoF) IoU -- not in the reference, which evaluates boxes_iou3d_gpu / nms_gpu on boxes[:, 0:7] and so
+ * ignores the pitch and roll Det6D predicts (point_head_box6d_vote.py:355, model_nms_utils.py:18).
+ * boxes (n, 9) [x, y, z, dx, dy, dz, rz, ry, rx] with R = Rx Ry Rz as pcdet/utils/box_utils.py:59-72 builds corners
+ * (scipy from_euler('zyx')); ans (na, nb) = volume(A n B) / max(vol A + vol B - volume(A n B), 1e-6). */
+int de6d_boxes_iou3d9(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, cudaStream_t stream);
 
 /* ---- roiaware_pool3d ---------------------------------------------------------------------------------- */
 

@@ -559,3 +559,178 @@ ORC_API void orc_points_in_boxes9(int t, int m, const float *boxes, const float 
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-pose (9-DoF) box intersection volume / IoU / NMS -- SURVEY.md 8(f) rank 3, second half.
+ * The reference has NO such function: PointHeadBox6DVote calls boxes_iou3d_gpu on boxes[:, 0:7]
+ * (point_head_box6d_vote.py:355) and class_agnostic_nms slices [:, 0:7] (model_nms_utils.py:18), i.e. pitch and roll
+ * are ignored.  Boxes follow box_utils.boxes3d_to_corners_3d (pcdet/utils/box_utils.py:59-72):
+ * [x, y, z, dx, dy, dz, rz, ry, rx], corners = R * (+-d/2) + centre with R = Rotation.from_euler('zyx', (rz, ry, rx))
+ * = Rx Ry Rz (the matrix orc_points_in_boxes9 uses, pinned against scipy there).
+ * Parity: pinned in tests/test_oracle.py against scipy.spatial (HalfspaceIntersection + ConvexHull volume, float64) and,
+ * for ry = rx = 0, against the reference's own boxes_iou3d_gpu composition (orc_boxes_iou3d).
+ *
+ * Algorithm (all double): work in box A's frame (A = [-ha, ha]^3 axis aligned) and clip the polyhedron A, kept as a list of
+ * convex face polygons, by B's six half-spaces one after the other (Sutherland-Hodgman per face).  The points where edges
+ * cross the clipping plane are collected -- computed from the inside vertex towards the outside vertex, so the two faces
+ * sharing an edge produce bit-identical points -- ordered by angle about their centroid and become the cap face on that
+ * plane.  By the divergence theorem V = 1/3 * sum over faces of (plane offset from A's centre) * (face area).  Because the
+ * cap is built from the very cut points that removed material, coplanar or nearly coplanar faces (identical boxes, padded
+ * duplicates, boxes sharing a ground plane) cost O(rounding), not a face counted twice.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { double x, y, z; } V3;
+#define B9_MAXV 16
+#define B9_MAXC 32
+
+static void box9_rot(const float *b, double r[9]) {
+    const double rz = b[6], ry = b[7], rx = b[8];
+    const double cz = cos(rz), sz = sin(rz), cy = cos(ry), sy = sin(ry), cx = cos(rx), sx = sin(rx);
+    r[0] = cy * cz;                 r[1] = -cy * sz;                r[2] = sy;
+    r[3] = sx * sy * cz + cx * sz;  r[4] = -sx * sy * sz + cx * cz; r[5] = -sx * cy;
+    r[6] = -cx * sy * cz + sx * sz; r[7] = cx * sy * sz + sx * cz;  r[8] = cx * cy;
+}
+
+static double poly_area(const V3 *p, int n) {
+    if (n < 3) return 0.0;
+    double ax = 0, ay = 0, az = 0;
+    for (int i = 1; i + 1 < n; ++i) {
+        const V3 u = {p[i].x - p[0].x, p[i].y - p[0].y, p[i].z - p[0].z}, v = {p[i + 1].x - p[0].x, p[i + 1].y - p[0].y, p[i + 1].z - p[0].z};
+        ax += u.y * v.z - u.z * v.y; ay += u.z * v.x - u.x * v.z; az += u.x * v.y - u.y * v.x;
+    }
+    return 0.5 * sqrt(ax * ax + ay * ay + az * az);
+}
+
+/* clip one face polygon (in place) by n.p <= d; cut points are appended to cp */
+static int clip_face(V3 *poly, int n, V3 nrm, double d, V3 *cp, int *ncp) {
+    V3 out[B9_MAXV];
+    double s[B9_MAXV];
+    int m = 0;
+    for (int i = 0; i < n; ++i) s[i] = nrm.x * poly[i].x + nrm.y * poly[i].y + nrm.z * poly[i].z - d;
+    for (int i = 0; i < n; ++i) {
+        const int k = (i + 1) % n;
+        const int pin = s[i] <= 0.0, qin = s[k] <= 0.0;
+        if (pin && m < B9_MAXV) out[m++] = poly[i];
+        if (pin != qin) {
+            const V3 a = pin ? poly[i] : poly[k], b = pin ? poly[k] : poly[i];   /* inside -> outside: same bits from both faces */
+            const double sa = pin ? s[i] : s[k], sb = pin ? s[k] : s[i];
+            const double t = sa / (sa - sb);
+            const V3 x = {a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z)};
+            if (m < B9_MAXV) out[m++] = x;
+            if (*ncp < B9_MAXC) cp[(*ncp)++] = x;
+        }
+    }
+    for (int i = 0; i < m; ++i) poly[i] = out[i];
+    return m;
+}
+
+/* order the cut points of one plane counter-clockwise about their centroid (in-plane basis u, v), drop exact duplicates */
+static int make_cap(V3 *cp, int n, V3 nrm, V3 *cap) {
+    if (n < 3) return 0;
+    V3 c = {0, 0, 0};
+    for (int i = 0; i < n; ++i) { c.x += cp[i].x; c.y += cp[i].y; c.z += cp[i].z; }
+    c.x /= n; c.y /= n; c.z /= n;
+    /* in-plane basis: u = normalised (nrm x e) with e the axis least aligned with nrm, v = nrm x u */
+    const double ax = fabs(nrm.x), ay = fabs(nrm.y), az = fabs(nrm.z);
+    V3 e = {0, 0, 0};
+    if (ax <= ay && ax <= az) e.x = 1; else if (ay <= az) e.y = 1; else e.z = 1;
+    V3 u = {nrm.y * e.z - nrm.z * e.y, nrm.z * e.x - nrm.x * e.z, nrm.x * e.y - nrm.y * e.x};
+    const double ul = sqrt(u.x * u.x + u.y * u.y + u.z * u.z);
+    u.x /= ul; u.y /= ul; u.z /= ul;
+    const V3 v = {nrm.y * u.z - nrm.z * u.y, nrm.z * u.x - nrm.x * u.z, nrm.x * u.y - nrm.y * u.x};
+    double ang[B9_MAXC];
+    for (int i = 0; i < n; ++i) {
+        const double px = cp[i].x - c.x, py = cp[i].y - c.y, pz = cp[i].z - c.z;
+        ang[i] = atan2(px * v.x + py * v.y + pz * v.z, px * u.x + py * u.y + pz * u.z);
+    }
+    for (int i = 1; i < n; ++i) {           /* insertion sort */
+        const double a = ang[i]; const V3 p = cp[i];
+        int k = i - 1;
+        while (k >= 0 && ang[k] > a) { ang[k + 1] = ang[k]; cp[k + 1] = cp[k]; --k; }
+        ang[k + 1] = a; cp[k + 1] = p;
+    }
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        if (m > 0 && cap[m - 1].x == cp[i].x && cap[m - 1].y == cp[i].y && cap[m - 1].z == cp[i].z) continue;
+        if (m < B9_MAXV) cap[m++] = cp[i];
+    }
+    if (m > 1 && cap[m - 1].x == cap[0].x && cap[m - 1].y == cap[0].y && cap[m - 1].z == cap[0].z) --m;
+    return m >= 3 ? m : 0;
+}
+
+ORC_API double orc_box9_intersection_volume(const float *a, const float *b) {
+    double ra[9], rb[9], m[9];
+    box9_rot(a, ra); box9_rot(b, rb);
+    /* m = ra^T rb: columns = B's axes in A's frame; t = ra^T (cb - ca) */
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) m[i * 3 + j] = ra[0 * 3 + i] * rb[0 * 3 + j] + ra[1 * 3 + i] * rb[1 * 3 + j] + ra[2 * 3 + i] * rb[2 * 3 + j];
+    const double dx = (double)b[0] - a[0], dy = (double)b[1] - a[1], dz = (double)b[2] - a[2];
+    const double t[3] = {ra[0] * dx + ra[3] * dy + ra[6] * dz, ra[1] * dx + ra[4] * dy + ra[7] * dz, ra[2] * dx + ra[5] * dy + ra[8] * dz};
+    const double ha[3] = {a[3] / 2.0, a[4] / 2.0, a[5] / 2.0}, hb[3] = {b[3] / 2.0, b[4] / 2.0, b[5] / 2.0};
+    if (!(ha[0] > 0 && ha[1] > 0 && ha[2] > 0 && hb[0] > 0 && hb[1] > 0 && hb[2] > 0)) return 0.0;
+    V3 face[12][B9_MAXV];
+    int nv[12];
+    double off[12];
+    /* the six faces of A, outward normal +-e_i, offset ha_i */
+    for (int i = 0; i < 3; ++i)
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            const int f = 2 * i + sgn, u = (i + 1) % 3, v = (i + 2) % 3;
+            const double s = sgn ? 1.0 : -1.0;
+            const double su[4] = {-1, 1, 1, -1}, sv[4] = {-1, -1, 1, 1};
+            for (int k = 0; k < 4; ++k) {
+                double c[3];
+                c[i] = s * ha[i]; c[u] = su[k] * ha[u]; c[v] = sv[k] * ha[v];
+                face[f][k].x = c[0]; face[f][k].y = c[1]; face[f][k].z = c[2];
+            }
+            nv[f] = 4; off[f] = ha[i];
+        }
+    int nf = 6;
+    for (int j = 0; j < 3; ++j)
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            const double s = sgn ? 1.0 : -1.0;
+            const V3 nr = {s * m[0 * 3 + j], s * m[1 * 3 + j], s * m[2 * 3 + j]};
+            const double d = hb[j] + (nr.x * t[0] + nr.y * t[1] + nr.z * t[2]);
+            V3 cp[B9_MAXC];
+            int ncp = 0;
+            for (int f = 0; f < nf; ++f)
+                if (nv[f] > 0) nv[f] = clip_face(face[f], nv[f], nr, d, cp, &ncp);
+            nv[nf] = make_cap(cp, ncp, nr, face[nf]);
+            off[nf] = d;
+            ++nf;
+        }
+    double vol3 = 0.0;
+    for (int f = 0; f < nf; ++f)
+        if (nv[f] >= 3) vol3 += off[f] * poly_area(face[f], nv[f]);
+    const double vol = vol3 / 3.0;
+    return vol > 0.0 ? vol : 0.0;
+}
+
+/* (na, 9) x (nb, 9) -> (na, nb) float: IoU = inter / max(va + vb - inter, 1e-6)  (the clamp of iou3d_nms_utils.py:79) */
+ORC_API void orc_boxes_iou3d_9dof(int na, const float *a, int nb, const float *b, float *out) {
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) {
+            const float *A = a + (size_t)i * 9, *B = b + (size_t)j * 9;
+            const double inter = orc_box9_intersection_volume(A, B);
+            const double va = (double)A[3] * A[4] * A[5], vb = (double)B[3] * B[4] * B[5];
+            double den = va + vb - inter;
+            if (den < 1e-6) den = 1e-6;
+            out[(size_t)i * nb + j] = (float)(inter / den);
+        }
+}
+
+/* greedy NMS over boxes sorted by descending score with the full-pose IoU (same sweep as orc_nms); returns num kept */
+ORC_API int orc_nms_9dof(int n, const float *boxes, float thresh, int64_t *keep) {
+    char *dead = (char *)calloc(n > 0 ? n : 1, 1);
+    int nk = 0;
+    for (int i = 0; i < n; ++i) {
+        if (dead[i]) continue;
+        keep[nk++] = i;
+        for (int j = i + 1; j < n; ++j) {
+            if (dead[j]) continue;
+            float v;
+            orc_boxes_iou3d_9dof(1, boxes + (size_t)i * 9, 1, boxes + (size_t)j * 9, &v);
+            if (v > thresh) dead[j] = 1;
+        }
+    }
+    free(dead);
+    return nk;
+}

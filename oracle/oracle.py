@@ -245,6 +245,34 @@ def points_in_boxes_cpu(points, boxes):
     return out
 
 
+def boxes_iou3d_9dof(a, b):
+    """Full-pose IoU: (N, 9) x (M, 9) [x, y, z, dx, dy, dz, rz, ry, rx] -> (N, M) float32 (double arithmetic inside)."""
+    a = _f32(a); b = _f32(b)
+    assert a.shape[1] == 9 and b.shape[1] == 9
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    lib().orc_boxes_iou3d_9dof(a.shape[0], _fp(a), b.shape[0], _fp(b), _fp(out))
+    return out
+
+
+def box9_intersection_volume(a, b):
+    a = _f32(a); b = _f32(b)
+    fn = lib().orc_box9_intersection_volume
+    fn.restype = C.c_double
+    return float(fn(_fp(a), _fp(b)))
+
+
+def nms_9dof(boxes, scores, thresh, pre_maxsize=None):
+    """Greedy NMS with the full-pose IoU; same calling convention as nms_gpu (returns indices into `boxes`)."""
+    boxes = _f32(boxes)
+    order = np.argsort(-np.asarray(scores, np.float32), kind="stable")
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    bs = np.ascontiguousarray(boxes[order])
+    keep = np.zeros(max(len(order), 1), np.int64)
+    nk = lib().orc_nms_9dof(len(order), _fp(bs), C.c_float(thresh), keep.ctypes.data_as(C.POINTER(C.c_int64)))
+    return order[keep[:nk]]
+
+
 def points_in_boxes3d(points, boxes3d):
     """box_utils.points_in_boxes3d (pcdet/utils/box_utils.py:110-124): points (n, 3+), boxes (m, 9) -> (n,) int64."""
     pts = _f32(np.asarray(points)[:, :3]); boxes = _f32(boxes3d)

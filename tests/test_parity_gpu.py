@@ -754,6 +754,89 @@ def test_class_agnostic_nms_batched_equals_reference_loop(orc, ops):
     np.testing.assert_array_equal(sel3[0, :int(num3[0])].cpu().numpy(), s3.cpu().numpy())
 
 
+def _boxes9(n, seed, cluster=8, tilt=0.35):
+    """Clustered full-pose proposals: `cluster` jittered copies per object so IoUs span (0, 1)."""
+    rng = np.random.default_rng(seed)
+    k = -(-n // cluster)
+    base = np.concatenate([rng.uniform(0, 40, (k, 1)), rng.uniform(-20, 20, (k, 1)), rng.uniform(-1.5, -0.5, (k, 1)),
+                           np.clip(rng.normal((3.9, 1.6, 1.56), 0.2, (k, 3)), 0.3, None), rng.uniform(-np.pi, np.pi, (k, 1)),
+                           rng.uniform(-tilt, tilt, (k, 2))], 1)
+    b = np.repeat(base, cluster, 0)[:n].copy()
+    b[:, :3] += rng.normal(0, 0.3, (n, 3)) * [1, 1, 0.3]
+    b[:, 3:6] *= rng.uniform(0.9, 1.1, (n, 3))
+    b[:, 6:] += rng.normal(0, 0.08, (n, 3))
+    return b.astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_full_pose_iou_vs_oracle(orc, ops, seed):
+    """boxes_iou3d_9dof_gpu (float, box9.cuh) against the oracle (double, pinned to scipy): 1e-4 relative (+1e-6), the same
+    zero pattern away from grazing contacts; identical / nested / face-sharing boxes; yaw-only boxes against boxes_iou3d_gpu."""
+    iu = ops[1]
+    a, b = _boxes9(300, seed), _boxes9(200, seed + 50)
+    b[:40] = a[:40]                                   # identical boxes (padded duplicates)
+    b[40:60] = a[40:60]; b[40:60, 3:6] *= 0.5         # nested
+    b[60:80] = a[60:80]; b[60:80, 3] *= 0.5           # shared face planes
+    got = iu.boxes_iou3d_9dof_gpu(cu(a), cu(b)).cpu().numpy()
+    want = orc.boxes_iou3d_9dof(a, b)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-6)
+    assert (want > 0.01).sum() > 300
+    np.testing.assert_allclose(np.diag(got)[:40], 1.0, atol=1e-5)
+    np.testing.assert_allclose(np.diag(got)[40:60], 0.125, atol=1e-5)
+    np.testing.assert_allclose(np.diag(got)[60:80], 0.5, atol=1e-5)
+    a7 = a.copy(); a7[:, 7:] = 0
+    i9 = iu.boxes_iou3d_9dof_gpu(cu(a7), cu(a7)).cpu().numpy()
+    i7 = iu.boxes_iou3d_gpu(cu(a7[:, :7]), cu(a7[:, :7])).cpu().numpy()
+    assert np.abs(i9 - i7).max() < 5e-3
+    assert iu.boxes_iou3d_9dof_gpu(cu(a[:0]), cu(b)).shape == (0, 200)
+
+
+@pytest.mark.parametrize("n,thr", [(512, 0.1), (512, 0.45), (200, 0.25), (64, 0.01), (700, 0.3)])
+def test_full_pose_nms_vs_oracle(orc, ops, n, thr):
+    """nms_gpu_9dof / the batched kernel in mode 2 against the oracle's greedy sweep with the same IoU, on seeds with no
+    pair within 1e-4 of the threshold."""
+    iu = ops[1]
+    checked = 0
+    for seed in range(6):
+        boxes = _boxes9(n, 10 * n + seed)
+        iou = orc.boxes_iou3d_9dof(boxes, boxes)
+        if (np.abs(iou - thr) < 1e-4).any():
+            continue
+        scores = np.random.default_rng(seed).permutation(n).astype(np.float32)
+        keep, none = iu.nms_gpu_9dof(cu(boxes), cu(scores), thr)
+        assert none is None
+        np.testing.assert_array_equal(keep.cpu().numpy(), orc.nms_9dof(boxes, scores, thr))
+        checked += 1
+    assert checked >= 3
+    # batched form, ragged nvalid, against per-frame calls
+    F = 5
+    bx = np.stack([_boxes9(n, 77 + f) for f in range(F)])
+    sc = np.stack([np.random.default_rng(f).permutation(n) for f in range(F)]).astype(np.float32)
+    keepb, numb = iu.nms_gpu_batched(cu(bx), cu(sc), thr)
+    for f in range(F):
+        k1, _ = iu.nms_gpu_9dof(cu(bx[f]), cu(sc[f]), thr)
+        assert int(numb[f]) == k1.numel() and torch.equal(keepb[f, :k1.numel()], k1)
+
+
+def test_class_agnostic_nms_full_pose(orc, ops):
+    """model_nms_utils with NMS_TYPE 'nms_gpu_9dof': single-frame form == batched form == oracle sweep on [:, 0:9]."""
+    from de6d_b200 import model_nms_utils as mu
+    n, F = 384, 3
+    cfg = {"NMS_TYPE": "nms_gpu_9dof", "NMS_THRESH": 0.2, "NMS_PRE_MAXSIZE": 300, "NMS_POST_MAXSIZE": 80}
+    preds = np.stack([np.concatenate([_boxes9(n, 5 + f), np.zeros((n, 1), np.float32)], 1) for f in range(F)])
+    scores = np.stack([np.random.default_rng(f).permutation(n) / n for f in range(F)]).astype(np.float32)
+    sel_b, sc_b, num_b = mu.class_agnostic_nms_batched(cu(scores), cu(preds), cfg, score_thresh=0.1)
+    for f in range(F):
+        sel, sc = mu.class_agnostic_nms(cu(scores[f]), cu(preds[f]), cfg, score_thresh=0.1)
+        k = int(num_b[f])
+        assert k == sel.numel() and torch.equal(sel_b[f, :k], sel) and torch.equal(sc_b[f, :k], sc)
+        m = scores[f] >= 0.1
+        idx = np.nonzero(m)[0]
+        top = idx[np.argsort(-scores[f][idx], kind="stable")][:300]
+        want = top[orc.nms_9dof(preds[f][top][:, :9], scores[f][top], 0.2)][:80]
+        np.testing.assert_array_equal(sel.cpu().numpy(), want)
+
+
 def test_points_in_boxes_vs_oracle(orc, ops):
     ru = ops[2]
     B, T, M = 3, 100, 16384
