@@ -55,6 +55,10 @@ PROTOTYPES = {
     "de6d_points_in_boxes_mask": [_i, _i, _p, _p, _p, _p],
     "de6d_points_in_boxes_mask_host": [_i, _i, _p, _p, _p, _i],
     "de6d_boxes_iou_bev_host": [_i, _p, _i, _p, _p, _i],
+    "de6d_sa_mlp_fits": [_i, _p, _i],
+    "de6d_sa_mlp_packed_floats": [_i, _p],
+    "de6d_sa_mlp_pack": [_i, _p, _p, _p, _p],
+    "de6d_sa_mlp_fused": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "de6d_stage_points": [_i, _i, _i, _i, C.c_longlong, _p, _p, _p, _p, _p, _p, _p],
     "de6d_last_error_string": [],
     "de6d_version": [],
@@ -65,11 +69,12 @@ _RESTYPES = {
     "de6d_nms_workspace_bytes": _sz,
     "de6d_ball_query_workspace_bytes": _sz,
     "de6d_ball_query_grid_bytes": _sz,
+    "de6d_sa_mlp_packed_floats": _sz,
     "de6d_last_error_string": C.c_char_p,
     "de6d_build_info": C.c_char_p,
     "de6d_launch_count": C.c_longlong,
 }
-_NO_STATUS = set(_RESTYPES) | {"de6d_version", "de6d_furthest_point_sampling_features_fits"}
+_NO_STATUS = set(_RESTYPES) | {"de6d_version", "de6d_furthest_point_sampling_features_fits", "de6d_sa_mlp_fits"}
 
 _lib = None
 

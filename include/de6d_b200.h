@@ -225,6 +225,26 @@ int de6d_points_in_boxes_mask(int t, int m, const float *boxes, const float *pts
  * (kitti_dataset.py:248, box_utils.py:104).  Bit-identical to the reference function.  Never touches the device. */
 int de6d_points_in_boxes_mask_host(int t, int m, const float *boxes, const float *pts, int *point_indices, int nthreads);
 
+/* ---- next to the path: one SA radius scale with the shared MLP fused behind the grouper ----------- */
+
+/* Replaces, per scale, groupers[i] -> mlps[i] -> idx_cnt mask -> max_pool2d of _PointnetSAModuleFSBase.forward
+ * (pointnet2_modules.py:461-478) after the ball query: gather, up to 4 [1x1 conv + folded BatchNorm + ReLU] layers on the
+ * tensor cores (tcgen05.mma kind::tf32, activations in tensor memory), empty-ball mask, max over nsample -- the grouped
+ * tensor (b, 3+c, m, nsample) and the hidden activations never reach HBM.
+ * widths (HOST int array, n_layers + 1): [3 + c_feat, c_1, ..., c_L]; every c_l a multiple of 16, <= 256; nsample a power
+ * of two in 4..128; all layers' tf32 weights must fit in shared memory (de6d_sa_mlp_fits tells).
+ * de6d_sa_mlp_pack: weights_cat (device) = the layers' BatchNorm-folded matrices, row-major [c_{l+1} x c_l], concatenated,
+ * layer 0's columns in the reference order (dx, dy, dz, features...); packed (device) = de6d_sa_mlp_packed_floats floats.
+ * de6d_sa_mlp_fused: xyz (b,n,3), new_xyz (b,m,3), feats_pm (b,n,c_feat) POINT-major features (NULL when c_feat == 0),
+ * idx (b,m,nsample), idx_cnt (b,m) or NULL, bias (device) = concatenated folded biases, out (b, c_L, m);
+ * status (device int, may be NULL) is set to 1 if a tensor-core wait timed out (never in a correct build). */
+int de6d_sa_mlp_fits(int n_layers, const int *widths, int nsample);
+size_t de6d_sa_mlp_packed_floats(int n_layers, const int *widths);
+int de6d_sa_mlp_pack(int n_layers, const int *widths, const float *weights_cat, float *packed, cudaStream_t stream);
+int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
+                      const float *feats_pm, const int *idx, const int *idx_cnt, int n_layers, const int *widths,
+                      const float *packed, const float *bias, float *out, int *status, cudaStream_t stream);
+
 /* ---- next to the path: full-pose boxes -------------------------------------------------- */
 
 /* box_utils.points_in_boxes3d(points, boxes3d)   pcdet/utils/box_utils.py:110-124 (host numpy + scipy Delaunay per box in
