@@ -468,6 +468,86 @@ def reference_cuda_leg(cfg, batch, dev, chain):
         return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
+def sa_mlp_leg(batch, dev):
+    """SA layers WITH their shared MLPs -- the reference composition (ball query -> grouped tensor in HBM
+    -> cuDNN 1x1 convs + BN + ReLU -> mask -> max-pool; TF32 convolutions, torch's and the reference's default) against the
+    fused kernel (ball query -> csrc/sa_mlp.cu: gather + tcgen05 tf32 MLP in tensor memory + mask + max-pool).  Layer shapes:
+    SASA / 3DSSD SA1 and SA2 (the scales whose weights fit in shared memory); random weights, eval-mode BatchNorm."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from de6d_b200 import pointnet2_utils as pu, sa_fused, synth
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf32_peak = float(json.load(f)["bf16_tflops"]) / 2.0
+        peak_src = "half the measured dense bf16 peak (MEASURED_PEAKS.json): tf32 runs at half the bf16 rate"
+    except Exception:
+        tf32_peak, peak_src = 1590.0 / 2.0, "half the fallback bf16 peak (B200_PROFILING.md)"
+    layers = {
+        "SA1 16384->4096, C=1": (16384, 4096, 1, [(0.2, 32, [16, 16, 32]), (0.4, 32, [16, 16, 32]), (0.8, 64, [32, 32, 64])]),
+        "SA2 4096->1024, C=64": (4096, 1024, 64, [(0.4, 32, [64, 64, 128]), (0.8, 32, [64, 64, 128]), (1.6, 64, [64, 96, 128])]),
+    }
+    out = {}
+    with torch.cuda.device(dev), torch.no_grad():
+        for name, (n, m, c, scales) in layers.items():
+            xyz = torch.from_numpy(synth.clouds(batch, n, seed=1)).to(dev)
+            new_xyz = xyz[:, :m].contiguous()
+            feats = torch.randn(batch, c, n, device=dev)
+            mods, fused, flops, grouped_bytes = [], [], 0.0, 0
+            for r, ns, mlp in scales:
+                widths = [c + 3] + mlp
+                seq = []
+                for a, b in zip(widths[:-1], widths[1:]):
+                    seq += [nn.Conv2d(a, b, 1, bias=False), nn.BatchNorm2d(b), nn.ReLU()]
+                    flops += 2.0 * a * b * batch * m * ns
+                seq = nn.Sequential(*seq).to(dev).eval()
+                mods.append((r, ns, seq))
+                fused.append(sa_fused.FusedSAScale(r, ns, seq))
+                grouped_bytes += 4 * (c + 3) * batch * m * ns
+            grid = pu.BallQueryGrid(xyz, min(r for r, _, _ in scales))
+            _, xyz_t = pu.gather_xyz(xyz, None)
+
+            def unfused():
+                res = []
+                for r, ns, seq in mods:
+                    cnt, idx = pu.ball_query_cnt(r, ns, xyz, new_xyz, grid=grid)
+                    g = pu.group_concat(xyz, new_xyz, feats, idx, xyz_t=xyz_t)
+                    y = seq(g) * (cnt > 0).float().unsqueeze(1).unsqueeze(-1)
+                    res.append(F.max_pool2d(y, kernel_size=[1, ns]).squeeze(-1))
+                return res
+
+            def fused_run():
+                fpm = feats.transpose(1, 2).contiguous()
+                return [fs(xyz, new_xyz, feats, grid=grid, feats_pm=fpm) for fs in fused]
+
+            def timeit(fn, reps=5):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                return e0.elapsed_time(e1) / reps
+            a, b2 = unfused(), fused_run()
+            err = max(float((x - y).abs().max() / x.abs().max()) for x, y in zip(a, b2))
+            del a, b2
+            t_un, t_fu = timeit(unfused), timeit(fused_run)
+            out[name] = {"unfused_ms": round(t_un, 3), "fused_ms": round(t_fu, 3), "speedup": round(t_un / t_fu, 2),
+                         "mlp_gflop": round(flops / 1e9, 1), "fused_tflops_incl_ball_query": round(flops / (t_fu * 1e-3) / 1e12, 1),
+                         "grouped_tensor_bytes_not_written": grouped_bytes, "max_rel_diff_vs_cudnn_tf32": round(err, 5)}
+            torch.cuda.empty_cache()
+    out["tensor_peak_tflops"] = tf32_peak
+    out["tensor_peak_source"] = peak_src
+    out["note"] = ("batch %d; unfused = ball_query_cnt (shared grid) + de6d_group_concat_t + torch Conv2d/BN/ReLU (cuDNN, allow_tf32) + mask + "
+                   "max_pool2d; fused = ball_query_cnt + de6d_sa_mlp_fused (+ one feature transposition per layer)" % batch)
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -570,6 +650,10 @@ def run_gpu_arm(args):
             del alt
             torch.cuda.empty_cache()
         line["reference_cuda"] = reference_cuda_leg(cfg, batch, dev, chain)
+        try:
+            line["sa_mlp_fused"] = sa_mlp_leg(batch, dev)
+        except Exception as e:  # noqa: BLE001
+            line["sa_mlp_fused"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
         others = {}
         for name in ("chain16", "stress131072"):
             if name == args.config:

@@ -24,9 +24,15 @@ def kernels_of(entry, shape):
         return ["dist_matrix_kernel"]
     if entry in ("de6d_gather_points", "de6d_group_points"):
         return ["group_"]
-    if entry == "de6d_group_concat":
-        return ["group_xyz_center_kernel", "group_"] if shape[1] > 0 else ["group_xyz_center_kernel"]
+    if entry in ("de6d_group_concat", "de6d_group_concat_t"):
+        return ["group_staged_kernel"]          # one launch: coordinate rows staged with the channels (r2)
+    if entry == "de6d_gather_xyz":
+        return ["gather_xyz_kernel"]
+    if entry == "de6d_ball_query_grid_build":
+        return ["bq_grid_build_kernel"]
     if entry == "de6d_ball_query_ex":
+        if shape[1] == 3:
+            return ["bq_grid_query_kernel"]     # grid built once per layer (de6d_ball_query_grid_build)
         return ["bq_grid_build_kernel", "bq_grid_query_kernel"] if shape[3] >= 2048 else ["ball_query_kernel"]
     if entry == "de6d_nms_batched":
         return ["nms_kernel"]

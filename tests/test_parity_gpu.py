@@ -787,7 +787,7 @@ def test_full_pose_iou_vs_oracle(orc, ops, seed):
     a7 = a.copy(); a7[:, 7:] = 0
     i9 = iu.boxes_iou3d_9dof_gpu(cu(a7), cu(a7)).cpu().numpy()
     i7 = iu.boxes_iou3d_gpu(cu(a7[:, :7]), cu(a7[:, :7])).cpu().numpy()
-    assert np.abs(i9 - i7).max() < 5e-3
+    assert np.abs(i9 - i7).max() < 1.5e-2      # the reference's BEV clipping pads its corner tests by 1e-2 m (iou3d_nms_kernel.cu:51-61)
     assert iu.boxes_iou3d_9dof_gpu(cu(a[:0]), cu(b)).shape == (0, 200)
 
 
