@@ -110,7 +110,10 @@ static inline int de6d_ensure_smem(F func, int bytes, unsigned long long &mask, 
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return DE6D_OK;
     cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return de6d_set_cuda_error(e, what);
+    if (e != cudaSuccess) {
+        cudaGetLastError();   // the failure is reported through the status code; do not leave it pending for the next CUDA user
+        return de6d_set_cuda_error(e, what);
+    }
     if (dev >= 0 && dev < 64) mask |= 1ull << dev;
     return DE6D_OK;
 }

@@ -320,7 +320,7 @@ static int sa_mlp_plan(int n_layers, const int *widths, int ns, SaMlpPlan &plan)
     for (int l = 0; l <= n_layers; ++l) p.col[l] = (l & 1) ? b0 : 0;
     plan.smem = 1024 + (size_t)p.w_bytes + (size_t)((p.bias_floats + 31) & ~31) * 4 + (size_t)p.width[n_layers] * SM_QTC * 4;
     if (plan.smem > 220 * 1024) return -5;                           // weights must stay resident in shared memory
-    int by_smem = (int)((227 * 1024) / (plan.smem + 1024));
+    int by_smem = (int)((226 * 1024) / (plan.smem + 1024));
     int by_tmem = 512 / cols;
     plan.ctas_per_sm = max(1, min(min(by_smem, by_tmem), 4));
     return 0;
@@ -379,7 +379,7 @@ extern "C" int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, c
     p.xyz = xyz; p.new_xyz = new_xyz; p.feats_pm = feats_pm; p.w_packed = packed; p.bias = bias; p.idx = idx; p.idx_cnt = idx_cnt;
     p.out = out; p.status = status;
     static unsigned long long devs = 0;
-    if (int rc = de6d_ensure_smem(sa_mlp_kernel, 227 * 1024, devs, "sa_mlp smem attribute")) return rc;
+    if (int rc = de6d_ensure_smem(sa_mlp_kernel, 226 * 1024, devs, "sa_mlp smem attribute")) return rc;   // 227 KB minus the static barriers
     const long long n_work = (long long)b * ceil_div(m, SM_QTC);
     long long grid = 148ll * plan.ctas_per_sm;
     if (grid > n_work) grid = n_work;

@@ -5,6 +5,8 @@ oracle/build_ref.py (oracle/_ref/*.so).
     python tests/golden/make_golden.py --cpu     # reference CPU entry points; runs anywhere the modules load
     python tests/golden/make_golden.py --cuda    # reference CUDA kernels; needs a GPU (run under gpurun),
                                                  # writes gpurun_out/golden_cuda.npz to be copied here
+    python tests/golden/make_golden.py --cuda2   # reference python wrappers (autograd, boxes_iou3d_gpu, groupers) over
+                                                 # the reference kernels -> gpurun_out/golden_cuda2.npz
 
 Inputs come from de6d_b200.synth with fixed seeds and are stored next to the outputs so the fixtures are
 self-contained (tests never regenerate them).  Sizes are kept small: the files are committed.
@@ -131,8 +133,66 @@ def cuda_vectors(ref):
     return out
 
 
+def cuda_vectors_wrappers():
+    """Second fixture (round 2): outputs of the reference's own PYTHON wrappers over its own kernels -- the rows the first
+    fixture lacks: boxes_iou3d_gpu (iou3d_nms_utils.py:48-81), gather / group forward AND backward (autograd Functions,
+    pointnet2_utils.py:115-149, 232-273), three_interpolate backward (:184-229), QueryWithCntAndGroup (:390-424)."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import ref_py
+    tree = ref_py.load_tree("pcdet_ref", build_ref.load())
+    pu, iu = tree.pointnet2_utils, tree.iou3d_nms_utils
+    dev = "cuda"
+    out = {}
+
+    def T(x):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+    bx, _ = synth.proposals(1, 160, seed=61, clusters=20)
+    a, b = bx[0][:80].copy(), bx[0][50:160].copy()
+    b[:, 2] += np.random.default_rng(6).normal(0, 0.4, len(b)).astype(np.float32)     # partial height overlaps
+    out.update(iou3d_a=a, iou3d_b=b, iou3d=iu.boxes_iou3d_gpu(T(a), T(b)).cpu().numpy())
+
+    B, C, N, M, ns = 2, 6, 700, 90, 8
+    rng = np.random.default_rng(7)
+    feats = synth.features(B, C, N, seed=62)
+    gidx = rng.integers(0, N, (B, M)).astype(np.int32)
+    f = T(feats).requires_grad_(True)
+    y = pu.gather_operation(f, T(gidx))
+    gy = torch.from_numpy(rng.normal(size=(B, C, M)).astype(np.float32)).to(dev)
+    y.backward(gy)
+    out.update(gg_feats=feats, gather_idx=gidx, gather_out=y.detach().cpu().numpy(), gather_gout=gy.cpu().numpy(),
+               gather_grad=f.grad.cpu().numpy())
+    qidx = rng.integers(0, N, (B, M, ns)).astype(np.int32)
+    f = T(feats).requires_grad_(True)
+    y = pu.grouping_operation(f, T(qidx))
+    gy = torch.from_numpy(rng.normal(size=(B, C, M, ns)).astype(np.float32)).to(dev)
+    y.backward(gy)
+    out.update(group_idx=qidx, group_out=y.detach().cpu().numpy(), group_gout=gy.cpu().numpy(), group_grad=f.grad.cpu().numpy())
+
+    m_known, n_unknown = 60, 150
+    kf = synth.features(B, C, m_known, seed=63)
+    tidx = rng.integers(0, m_known, (B, n_unknown, 3)).astype(np.int32)
+    tw = rng.uniform(0, 1, (B, n_unknown, 3)).astype(np.float32)
+    tw /= tw.sum(-1, keepdims=True)
+    f = T(kf).requires_grad_(True)
+    y = pu.three_interpolate(f, T(tidx), T(tw))
+    gy = torch.from_numpy(rng.normal(size=(B, C, n_unknown)).astype(np.float32)).to(dev)
+    y.backward(gy)
+    out.update(ti2_feats=kf, ti2_idx=tidx, ti2_weight=tw, ti2_out=y.detach().cpu().numpy(), ti2_gout=gy.cpu().numpy(),
+               ti2_grad=f.grad.cpu().numpy())
+
+    xyz = synth.lidar_clouds(B, N, seed=64)
+    new_xyz = np.ascontiguousarray(xyz[:, ::7][:, :M]) + np.float32(0.02)
+    new_xyz[:, -2:] += 300.0
+    cnt, nf = pu.QueryWithCntAndGroup(1.5, ns)(T(xyz), T(new_xyz), T(feats))
+    out.update(qg_xyz=xyz, qg_new_xyz=new_xyz, qg_cnt=cnt.cpu().numpy(), qg_out=nf.cpu().numpy())
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--cuda2", action="store_true", help="reference python wrappers over the reference kernels (needs a GPU)")
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--cuda", action="store_true")
     ap.add_argument("--out", default=None)
@@ -143,6 +203,11 @@ def main():
     if args.cpu:
         path = args.out or os.path.join(here, "golden_cpu.npz")
         np.savez_compressed(path, **cpu_vectors(ref))
+        print("wrote", path)
+    if args.cuda2:
+        path = os.path.join(ROOT, "gpurun_out", "golden_cuda2.npz")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.savez_compressed(path, **cuda_vectors_wrappers())
         print("wrote", path)
     if args.cuda:
         path = args.out or os.path.join(ROOT, "gpurun_out", "golden_cuda.npz")

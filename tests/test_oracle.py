@@ -259,3 +259,24 @@ def test_full_pose_iou_oracle_vs_scipy(orc):
     assert (i7 > 1e-3).sum() > 500 and np.abs(i9 - i7).max() < 5e-3
     keep = orc.nms_9dof(A, np.arange(60, 0, -1, dtype=np.float32), 0.1)
     assert keep[0] == 0 and 1 < len(keep) < 60
+
+
+def test_oracle_vs_reference_wrapper_golden(orc, golden_dir):
+    """Second fixture: the reference's python wrappers over its own kernels (tests/golden/make_golden.py --cuda2):
+    boxes_iou3d_gpu, gather / group / three_interpolate forward + backward, QueryWithCntAndGroup."""
+    g = _load(golden_dir, "golden_cuda2.npz")
+    iou = orc.boxes_iou3d(g["iou3d_a"], g["iou3d_b"])
+    assert (g["iou3d"] > 0.01).sum() > 40
+    np.testing.assert_allclose(iou, g["iou3d"], rtol=1e-5, atol=1e-7)
+    N = g["gg_feats"].shape[2]
+    np.testing.assert_array_equal(orc.gather_operation(g["gg_feats"], g["gather_idx"]), g["gather_out"])
+    np.testing.assert_allclose(orc.gather_operation_grad(g["gather_gout"], g["gather_idx"], N), g["gather_grad"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(orc.grouping_operation(g["gg_feats"], g["group_idx"]), g["group_out"])
+    np.testing.assert_allclose(orc.grouping_operation_grad(g["group_gout"], g["group_idx"], N), g["group_grad"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(orc.three_interpolate(g["ti2_feats"], g["ti2_idx"], g["ti2_weight"]), g["ti2_out"])
+    np.testing.assert_allclose(orc.three_interpolate_grad(g["ti2_gout"], g["ti2_idx"], g["ti2_weight"], g["ti2_feats"].shape[2]),
+                               g["ti2_grad"], rtol=1e-5, atol=1e-5)
+    cnt, idx = orc.ball_query_cnt(1.5, g["group_idx"].shape[2], g["qg_xyz"], g["qg_new_xyz"])
+    np.testing.assert_array_equal(cnt, g["qg_cnt"])
+    gx = orc.grouping_operation(np.ascontiguousarray(g["qg_xyz"].transpose(0, 2, 1)), idx) - g["qg_new_xyz"].transpose(0, 2, 1)[..., None]
+    np.testing.assert_array_equal(np.concatenate([gx, orc.grouping_operation(g["gg_feats"], idx)], 1), g["qg_out"])

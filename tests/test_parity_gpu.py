@@ -794,13 +794,13 @@ def test_full_pose_iou_vs_oracle(orc, ops, seed):
 @pytest.mark.parametrize("n,thr", [(512, 0.1), (512, 0.45), (200, 0.25), (64, 0.01), (700, 0.3)])
 def test_full_pose_nms_vs_oracle(orc, ops, n, thr):
     """nms_gpu_9dof / the batched kernel in mode 2 against the oracle's greedy sweep with the same IoU, on seeds with no
-    pair within 1e-4 of the threshold."""
+    pair within 2e-5 of the threshold."""
     iu = ops[1]
     checked = 0
-    for seed in range(6):
+    for seed in range(10):
         boxes = _boxes9(n, 10 * n + seed)
         iou = orc.boxes_iou3d_9dof(boxes, boxes)
-        if (np.abs(iou - thr) < 1e-4).any():
+        if (np.abs(iou - thr) < 2e-5).any():       # float kernel vs double oracle: |diff| <= 1e-4 * iou asserted above, ~1e-6 typical
             continue
         scores = np.random.default_rng(seed).permutation(n).astype(np.float32)
         keep, none = iu.nms_gpu_9dof(cu(boxes), cu(scores), thr)
@@ -918,6 +918,34 @@ def test_against_reference_cuda_golden(golden, ops, lib):
 
 
 # ------------------------------------------------------------------------------------------------ live reference kernels (when built)
+def test_against_reference_wrapper_golden(golden_dir, ops):
+    """This library's kernels against the second committed fixture (reference python wrappers over the reference kernels):
+    fused boxes_iou3d_gpu, gather / group / three_interpolate with gradients, the fused QueryWithCntAndGroup tail."""
+    p = os.path.join(golden_dir, "golden_cuda2.npz")
+    if not os.path.exists(p):
+        pytest.skip("golden_cuda2.npz not generated yet")
+    g = np.load(p)
+    pu, iu, _ = ops
+    np.testing.assert_allclose(iu.boxes_iou3d_gpu(cu(g["iou3d_a"]), cu(g["iou3d_b"])).cpu().numpy(), g["iou3d"], rtol=RTOL_IOU, atol=1e-7)
+    for fn, idx_key, out_key, gout_key, grad_key in (("gather_operation", "gather_idx", "gather_out", "gather_gout", "gather_grad"),
+                                                      ("grouping_operation", "group_idx", "group_out", "group_gout", "group_grad")):
+        f = cu(g["gg_feats"]).requires_grad_(True)
+        with torch.enable_grad():
+            y = getattr(pu, fn)(f, cu(g[idx_key]))
+            y.backward(cu(g[gout_key]))
+        np.testing.assert_array_equal(y.detach().cpu().numpy(), g[out_key])
+        np.testing.assert_allclose(f.grad.cpu().numpy(), g[grad_key], rtol=1e-5, atol=1e-5)
+    f = cu(g["ti2_feats"]).requires_grad_(True)
+    with torch.enable_grad():
+        y = pu.three_interpolate(f, cu(g["ti2_idx"]), cu(g["ti2_weight"]))
+        y.backward(cu(g["ti2_gout"]))
+    np.testing.assert_array_equal(y.detach().cpu().numpy(), g["ti2_out"])
+    np.testing.assert_allclose(f.grad.cpu().numpy(), g["ti2_grad"], rtol=1e-5, atol=1e-5)
+    cnt, nf = pu.QueryWithCntAndGroup(1.5, g["group_idx"].shape[2])(cu(g["qg_xyz"]), cu(g["qg_new_xyz"]), cu(g["gg_feats"]))
+    np.testing.assert_array_equal(cnt.cpu().numpy(), g["qg_cnt"])
+    np.testing.assert_array_equal(nf.cpu().numpy(), g["qg_out"])
+
+
 def test_against_live_reference_kernels(ref_modules, ops, lib):
     if ref_modules is None:
         pytest.skip("oracle/_ref not available on this box")
