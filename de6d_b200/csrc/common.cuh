@@ -103,17 +103,18 @@ void de6d_count_launch(void);
     } while (0)
 
 // Dynamic shared memory above 48 KB is an opt-in attribute of a (function, device) pair: set it once per pair.
-// `mask` is a per-call-site static bit set of the devices already configured (race-benign: setting twice is harmless).
+// `mask` is a per-call-site static bit set of the devices already configured, read and updated atomically (entry points
+// may be called from several host threads; setting the attribute twice is harmless, losing a bit only repeats it).
 template <typename F>
 static inline int de6d_ensure_smem(F func, int bytes, unsigned long long &mask, const char *what) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return DE6D_OK;
+    if (dev >= 0 && dev < 64 && ((__atomic_load_n(&mask, __ATOMIC_RELAXED) >> dev) & 1ull)) return DE6D_OK;
     cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();   // the failure is reported through the status code; do not leave it pending for the next CUDA user
         return de6d_set_cuda_error(e, what);
     }
-    if (dev >= 0 && dev < 64) mask |= 1ull << dev;
+    if (dev >= 0 && dev < 64) __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELAXED);
     return DE6D_OK;
 }

@@ -267,7 +267,7 @@ def test_oracle_vs_reference_wrapper_golden(orc, golden_dir):
     g = _load(golden_dir, "golden_cuda2.npz")
     iou = orc.boxes_iou3d(g["iou3d_a"], g["iou3d_b"])
     assert (g["iou3d"] > 0.01).sum() > 40
-    np.testing.assert_allclose(iou, g["iou3d"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(iou, g["iou3d"], rtol=1e-5, atol=1e-6)      # grazing overlaps (IoU ~ 1e-3) carry absolute, not relative, noise
     N = g["gg_feats"].shape[2]
     np.testing.assert_array_equal(orc.gather_operation(g["gg_feats"], g["gather_idx"]), g["gather_out"])
     np.testing.assert_allclose(orc.gather_operation_grad(g["gather_gout"], g["gather_idx"], N), g["gather_grad"], rtol=1e-5, atol=1e-6)

@@ -4,8 +4,9 @@ against the reference composition groupers[i] -> mlps[i] -> mask -> max_pool2d o
 Two comparisons per shape:
   * EXACT ARITHMETIC CHECK: a float64 evaluation of the same network whose operands are rounded to tf32 exactly where the
     kernel rounds them (inputs, BN-folded weights, hidden activations; cvt.rna).  Products of tf32 numbers are exact in
-    fp32 and the kernel accumulates in fp32, so it must agree to fp32 accumulation noise: 2e-5 relative to the largest
-    activation.  This pins the gather, the layer chaining through tensor memory, the mask and the pooling.
+    fp32 and the kernel accumulates in fp32, so it must agree to fp32 accumulation noise (median error <= 1e-5 of the largest
+    activation; single layer: maximum <= 2e-5) plus, in deeper nets, rare tf32 rounding flips of hidden activations (maximum
+    <= 5e-4).  This pins the gather, the layer chaining through tensor memory, the mask and the pooling.
   * REFERENCE CHECK: torch's own Conv2d / BatchNorm2d(eval) / ReLU / max_pool2d in fp32 (allow_tf32 off).  The kernel
     computes in tf32 like the reference's default cuDNN path (torch.backends.cudnn.allow_tf32 = True), so the bar is the
     tf32 one: 1e-3 of the largest activation per layer of depth (north_star allows tensor cores only here).
@@ -101,9 +102,14 @@ def test_fused_scale_vs_exact_tf32_and_torch(lib, B, N, M, ns, widths, radius):
     top = float(exact.abs().max())
     assert top > 0.1
     assert got.shape == ref.shape == (B, widths[-1], M)
-    err_exact = float((got - exact).abs().max())
+    d_exact = (got - exact).abs()
+    err_exact, med_exact = float(d_exact.max()), float(d_exact.median())
     err_ref = float((got - ref).abs().max())
-    assert err_exact <= 2e-5 * top, "vs tf32-exact evaluation: %g of %g" % (err_exact, top)
+    # single layer: fp32 accumulation noise only.  Deeper nets: a hidden activation that lands within fp32 noise of a tf32
+    # rounding boundary may round the other way than in the float64 evaluation (one tf32 ulp = 2^-10 of that activation, in
+    # ~1e-3 of the activations), so the MAXIMUM carries those flips while the median stays at accumulation noise.
+    assert med_exact <= 1e-5 * top, "vs tf32-exact evaluation (median): %g of %g" % (med_exact, top)
+    assert err_exact <= (2e-5 if len(widths) == 2 else 5e-4) * top, "vs tf32-exact evaluation (max): %g of %g" % (err_exact, top)
     assert err_ref <= 1e-3 * (len(widths) - 1) * top, "vs torch fp32: %g of %g" % (err_ref, top)
     assert float(got[:, :, -3:].abs().max()) == 0.0                             # empty balls
     assert bool((got >= 0).all())
