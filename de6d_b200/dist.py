@@ -45,6 +45,30 @@ def gather_detections(keep: torch.Tensor, num: torch.Tensor, frames_per_rank: in
     return keep_all, num_all
 
 
+def gather_detection_boxes(boxes: torch.Tensor, scores: torch.Tensor, keep: torch.Tensor, num: torch.Tensor):
+    """The end-of-batch collective SURVEY.md 8(e) describes: every rank contributes fixed-shape padded detections
+    (F_local, K, D) boxes + (F_local, K) scores + (F_local,) counts and receives the whole batch's (replaces the reference's
+    pickle files on a shared filesystem between two barriers, pcdet/utils/common_utils.py:212-233).
+    boxes (F_local, n, D), scores (F_local, n): the frame's proposals; keep (F_local, K) int64 kept indices padded beyond
+    num[f]; num (F_local,) int32.  Returns (boxes_all (world*F_local, K, D), scores_all (world*F_local, K), num_all); rows
+    beyond num are zero.  Three all_gather_into_tensor calls, no host synchronisation; with world == 1 no collective."""
+    F, K = keep.shape
+    valid = torch.arange(K, device=keep.device).unsqueeze(0) < num.unsqueeze(1)
+    kc = keep.clamp(min=0)
+    det_boxes = torch.gather(boxes, 1, kc.unsqueeze(-1).expand(-1, -1, boxes.size(2))) * valid.unsqueeze(-1)
+    det_scores = torch.gather(scores, 1, kc) * valid
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return det_boxes, det_scores, num
+    world = dist.get_world_size()
+    boxes_all = torch.empty((world * F, K, boxes.size(2)), dtype=boxes.dtype, device=boxes.device)
+    scores_all = torch.empty((world * F, K), dtype=scores.dtype, device=scores.device)
+    num_all = torch.empty((world * F,), dtype=num.dtype, device=num.device)
+    dist.all_gather_into_tensor(boxes_all, det_boxes.contiguous())
+    dist.all_gather_into_tensor(scores_all, det_scores.contiguous())
+    dist.all_gather_into_tensor(num_all, num.contiguous())
+    return boxes_all, scores_all, num_all
+
+
 def max_over_ranks(value: float, device=None) -> float:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return value

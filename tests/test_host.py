@@ -40,8 +40,13 @@ def _gloo_worker(rank, world, port, total, q):
         keep[i, : (f % 4) + 1] = torch.arange(f, f + (f % 4) + 1); num[i] = (f % 4) + 1
     keep_all, num_all = ddist.gather_detections(keep, num)
     t = ddist.max_over_ranks(float(rank + 1))
+    # the full detection gather: boxes of frame f are f + 0.01 * proposal index, scores the proposal index
+    boxes = torch.stack([(f + 0.01 * torch.arange(16, dtype=torch.float32)).unsqueeze(1).expand(16, 7) for f in range(lo, hi)])
+    scores = torch.arange(16, dtype=torch.float32).unsqueeze(0).expand(hi - lo, 16).contiguous()
+    kidx = torch.stack([torch.arange(4) + (f % 3) for f in range(lo, hi)])
+    b_all, s_all, n_all = ddist.gather_detection_boxes(boxes, scores, kidx, num)
     if rank == 0:
-        q.put((keep_all.numpy(), num_all.numpy(), t))
+        q.put((keep_all.numpy(), num_all.numpy(), t, b_all.numpy(), s_all.numpy(), n_all.numpy()))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -53,7 +58,7 @@ def test_gather_detections_gloo_world2():
     procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, total, q)) for r in range(world)]
     for p in procs:
         p.start()
-    keep_all, num_all, t = q.get(timeout=120)
+    keep_all, num_all, t, b_all, s_all, n_all = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -63,6 +68,11 @@ def test_gather_detections_gloo_world2():
         n = (f % 4) + 1
         assert num_all[f] == n
         np.testing.assert_array_equal(keep_all[f, :n], np.arange(f, f + n))
+        assert n_all[f] == n and b_all.shape == (6, 4, 7) and s_all.shape == (6, 4)
+        want = np.arange(4) + (f % 3)
+        np.testing.assert_allclose(s_all[f, :n], want[:n])
+        np.testing.assert_allclose(b_all[f, :n, 0], f + 0.01 * want[:n], rtol=1e-6)
+        assert (b_all[f, n:] == 0).all() and (s_all[f, n:] == 0).all()
 
 
 def test_chain_config_shapes():
