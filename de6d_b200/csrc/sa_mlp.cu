@@ -98,12 +98,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
                  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-                 "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-                 : "memory");
+                 "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]));
 }
+// (no "memory" clobber on the tensor-memory stores: they touch no C++ object, their order against tcgen05.wait::st and the
+// fences is kept by `volatile`, and without the clobber the compiler may keep independent global loads in flight across them)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
-                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
 
 // Packs one layer's BN-folded weights (row-major [n_out x k_in], device) into the tf32-rounded SWIZZLE_128B image the
@@ -122,7 +123,7 @@ __global__ void sa_mlp_pack_kernel(int n_out, int k_in, int k_pad32, int xyz_las
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 sa_mlp_kernel(const SaMlpParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t bar_w, bar_mma;
@@ -169,13 +170,22 @@ sa_mlp_kernel(const SaMlpParams p) {
 
     for (int work = blockIdx.x; work < n_work && ok; work += gridDim.x) {
         const int bi = work / wpb, q0 = (work - bi * wpb) * SM_QTC;
+        int k_next;
+        {
+            const int ql0 = tid / p.ns, qq = q0 + ql0;
+            k_next = qq < p.m ? __ldg(p.idx + ((size_t)bi * p.m + qq) * p.ns + (tid - ql0 * p.ns)) : 0;
+        }
         for (int t = 0; t < tiles; ++t) {
             // ---- gather: this thread's grouped point -> TMEM lane `tid`, columns [col[0], col[0] + width[0]) ----
             const int g = t * 128 + tid;
-            const int ql = g / p.ns, s = g - ql * p.ns;
+            const int ql = g / p.ns;
             const int q = q0 + ql;
             const bool valid = q < p.m;
-            int k = valid ? p.idx[((size_t)bi * p.m + q) * p.ns + s] : 0;
+            int k = k_next;
+            {   // the next tile's index is requested now, a whole tile of work before it is needed
+                const int g2 = (t + 1) * 128 + tid, ql2 = g2 / p.ns, q2 = q0 + ql2;
+                k_next = (t + 1 < tiles && q2 < p.m) ? __ldg(p.idx + ((size_t)bi * p.m + q2) * p.ns + (g2 - ql2 * p.ns)) : 0;
+            }
             k = min(max(k, 0), p.n - 1);
             const float *frow = p.feats_pm + ((size_t)bi * p.n + k) * C;
             const float *prow = p.xyz + ((size_t)bi * p.n + k) * 3;
@@ -183,7 +193,26 @@ sa_mlp_kernel(const SaMlpParams p) {
             const float rel[3] = {__fsub_rn(__ldg(prow), __ldg(crow)), __fsub_rn(__ldg(prow + 1), __ldg(crow + 1)),
                                   __fsub_rn(__ldg(prow + 2), __ldg(crow + 2))};
             const bool vec = (C & 3) == 0;
-            for (int c0 = 0; c0 < p.width[0]; c0 += 8) {
+            // feature columns in batches of 32: eight 16-byte loads are issued before the first conversion, so a row costs
+            // ~C/32 L2 round trips instead of C/8
+            int c0 = 0;
+            if (vec) {
+                for (; c0 + 32 <= C; c0 += 32) {
+                    float4 f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = __ldg(reinterpret_cast<const float4 *>(frow + c0) + j);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        uint32_t v[8];
+                        v[0] = __float_as_uint(to_tf32(f[2 * h].x)); v[1] = __float_as_uint(to_tf32(f[2 * h].y));
+                        v[2] = __float_as_uint(to_tf32(f[2 * h].z)); v[3] = __float_as_uint(to_tf32(f[2 * h].w));
+                        v[4] = __float_as_uint(to_tf32(f[2 * h + 1].x)); v[5] = __float_as_uint(to_tf32(f[2 * h + 1].y));
+                        v[6] = __float_as_uint(to_tf32(f[2 * h + 1].z)); v[7] = __float_as_uint(to_tf32(f[2 * h + 1].w));
+                        tmem_st8(lane_addr + (uint32_t)(p.col[0] + c0 + 8 * h), v);
+                    }
+                }
+            }
+            for (; c0 < p.width[0]; c0 += 8) {
                 uint32_t v[8];
                 if (vec && c0 + 8 <= C) {
                     const float4 a = __ldg(reinterpret_cast<const float4 *>(frow + c0));
@@ -229,10 +258,14 @@ sa_mlp_kernel(const SaMlpParams p) {
                     // hidden layer: bias + ReLU + tf32 rounding, in place (next layer's A operand)
                     for (int c0 = 0; c0 < nout; c0 += 16) {
                         uint32_t v[16];
+                        float bb[16];
                         tmem_ld16(lane_addr + (uint32_t)(p.col[l + 1] + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)    // four broadcast 16-byte loads while the tensor-memory load is in flight
+                            *reinterpret_cast<float4 *>(bb + 4 * j) = *reinterpret_cast<const float4 *>(bias + c0 + 4 * j);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f)));
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f)));
                         tmem_st16(lane_addr + (uint32_t)(p.col[l + 1] + c0), v);
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -243,11 +276,15 @@ sa_mlp_kernel(const SaMlpParams p) {
                     const bool leader = (lane & (seg - 1)) == 0;
                     for (int c0 = 0; c0 < nout; c0 += 16) {
                         uint32_t v[16];
+                        float bb[16];
                         tmem_ld16(lane_addr + (uint32_t)(p.col[l + 1] + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4 *>(bb + 4 * j) = *reinterpret_cast<const float4 *>(bias + c0 + 4 * j);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float y = live ? fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f) : 0.f;
+                            const float y = live ? fmaxf(__uint_as_float(v[j]) + bb[j], 0.f) : 0.f;
                             uint32_t u = __float_as_uint(y);               // y >= +0: unsigned order == float order
                             if (seg == 32) {
                                 u = __reduce_max_sync(0xffffffffu, u);
