@@ -11,14 +11,15 @@
 // The ball query itself stays the existing kernel (its idx / idx_cnt are inputs here).
 //
 // Mapping.  A tile is 128 grouped points (128 / nsample consecutive queries of one cloud) = the M dimension of one
-// tcgen05.mma (cta_group::1, M = 128): TMEM lane r <-> grouped point r <-> thread r of the 128-thread CTA.
+// tcgen05.mma (cta_group::1, M = 128): TMEM lane r <-> grouped point r <-> threads r and r + 128 of the 256-thread CTA (the two
+// split the columns).
 //   gather   thread r reads its point's feature row (point-major copy of the features, (B, N, C): one contiguous row per
-//            gathered point instead of C sectors) and its centred coordinates, rounds to tf32 (cvt.rna, what cuDNN's TF32
-//            convolutions do) and writes them with tcgen05.st straight into TMEM as the A operand -- the gathered tile
-//            never exists in shared memory either;
+//            gathered point instead of C sectors) and its centred coordinates and writes them with tcgen05.st straight into
+//            TMEM as the A operand (fp32 bits; the tensor core reads the upper 19 = tf32 by truncation, as for cuDNN's TF32
+//            convolutions) -- the gathered tile never exists in shared memory either;
 //   layer l  one thread issues K_l / 8 tcgen05.mma (A from TMEM, B = the layer's weights resident in shared memory as a
 //            SWIZZLE_128B K-major image, D in TMEM), tcgen05.commit -> mbarrier;
-//   epilogue every thread reads its lane of D with tcgen05.ld, adds the folded BN bias, applies ReLU, rounds to tf32 and
+//   epilogue every thread reads its lane of D with tcgen05.ld, adds the folded BN bias, applies ReLU and
 //            stores it back IN PLACE as the next layer's A operand; after the last layer it applies the idx_cnt mask and
 //            reduces over the nsample lanes of each query (REDUX on the float bits -- the values are >= 0 after ReLU --
 //            or shuffles for nsample < 32, shared-memory atomicMax across warps for nsample > 32);
@@ -27,7 +28,8 @@
 // whose weights do not fit (e.g. 131 -> 128 -> 128 -> 256: 272 KB in tf32) are refused (DE6D_ERR_INVALID) and the caller
 // keeps the unfused composition.  TMEM columns are ping-ponged between two buffers (input / output of a layer).
 //
-// Numerics: tf32 operands (10-bit mantissa, round-to-nearest), fp32 accumulation -- the arithmetic of the reference's own
+// Numerics: tf32 operands (10-bit mantissa; weights rounded to nearest when packed, activations truncated by the tensor core),
+// fp32 accumulation -- the arithmetic of the reference's own
 // default (torch.backends.cudnn.allow_tf32 = True for Conv2d); BN is folded into the weights before the rounding.
 #include "common.cuh"
 
@@ -123,13 +125,21 @@ __global__ void sa_mlp_pack_kernel(int n_out, int k_in, int k_pad32, int xyz_las
     }
 }
 
-__global__ void __launch_bounds__(128, 4)
+// T = 256 threads: warps w and w + 4 serve the same quarter of the tensor-memory lanes (a warp may only touch lanes
+// 32 * (w % 4) ...) and split the COLUMNS of every gather / epilogue between them, so 16 warps per SM are in flight at two
+// CTAs per SM.  MINB = CTAs per SM the register allocation must allow (4 for small nets, 2 for nets that fill tensor memory).
+constexpr int SM_T = 256;
+
+template <int MINB>
+__global__ void __launch_bounds__(SM_T, MINB)
 sa_mlp_kernel(const SaMlpParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t bar_w, bar_mma;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_fail;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quarter = warp & 3, half = warp >> 2;          // lane quarter of the tile, column half of the work
+    const int row = quarter * 32 + lane;                     // this thread's grouped point within a tile
     unsigned char *sW = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
     float *sBias = reinterpret_cast<float *>(sW + p.w_bytes);
     const int c_out = p.width[p.n_layers];
@@ -145,8 +155,8 @@ sa_mlp_kernel(const SaMlpParams p) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < p.bias_floats; i += 128) sBias[i] = p.bias[i];
-    for (int i = tid; i < c_out * SM_QTC; i += 128) sOut[i] = 0u;
+    for (int i = tid; i < p.bias_floats; i += SM_T) sBias[i] = p.bias[i];
+    for (int i = tid; i < c_out * SM_QTC; i += SM_T) sOut[i] = 0u;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -158,7 +168,7 @@ sa_mlp_kernel(const SaMlpParams p) {
         }
     }
     const uint32_t tbase = tmem_base_s;
-    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
     bool ok = mbar_wait_bounded(&bar_w, 0);
     uint32_t mma_phase = 0;
 
@@ -167,58 +177,64 @@ sa_mlp_kernel(const SaMlpParams p) {
     const int tiles = SM_QTC * p.ns / 128;                     // tiles per work item (host guarantees divisibility)
     const int C = p.c_feat;
     const int K = C + 3;
+    // this thread's share of the input columns: [cs, ce), split at a multiple of 32 (or 8 for narrow inputs)
+    const int W0 = p.width[0];
+    const int split = W0 >= 64 ? ((W0 / 2) & ~31) : ((W0 / 2 + 7) & ~7);
+    const int cs = half ? split : 0, ce = half ? W0 : split;
 
     for (int work = blockIdx.x; work < n_work && ok; work += gridDim.x) {
         const int bi = work / wpb, q0 = (work - bi * wpb) * SM_QTC;
         int k_next;
         {
-            const int ql0 = tid / p.ns, qq = q0 + ql0;
-            k_next = qq < p.m ? __ldg(p.idx + ((size_t)bi * p.m + qq) * p.ns + (tid - ql0 * p.ns)) : 0;
+            const int ql0 = row / p.ns, qq = q0 + ql0;
+            k_next = qq < p.m ? __ldg(p.idx + ((size_t)bi * p.m + qq) * p.ns + (row - ql0 * p.ns)) : 0;
         }
         for (int t = 0; t < tiles; ++t) {
-            // ---- gather: this thread's grouped point -> TMEM lane `tid`, columns [col[0], col[0] + width[0]) ----
-            const int g = t * 128 + tid;
+            // ---- gather: grouped point `row` -> TMEM lane `row`, this thread's columns of [col[0], col[0] + width[0]) ----
+            const int g = t * 128 + row;
             const int ql = g / p.ns;
             const int q = q0 + ql;
             const bool valid = q < p.m;
             int k = k_next;
             {   // the next tile's index is requested now, a whole tile of work before it is needed
-                const int g2 = (t + 1) * 128 + tid, ql2 = g2 / p.ns, q2 = q0 + ql2;
+                const int g2 = (t + 1) * 128 + row, ql2 = g2 / p.ns, q2 = q0 + ql2;
                 k_next = (t + 1 < tiles && q2 < p.m) ? __ldg(p.idx + ((size_t)bi * p.m + q2) * p.ns + (g2 - ql2 * p.ns)) : 0;
             }
             k = min(max(k, 0), p.n - 1);
             const float *frow = p.feats_pm + ((size_t)bi * p.n + k) * C;
-            const float *prow = p.xyz + ((size_t)bi * p.n + k) * 3;
-            const float *crow = p.new_xyz + ((size_t)bi * p.m + (valid ? q : 0)) * 3;
-            const float rel[3] = {__fsub_rn(__ldg(prow), __ldg(crow)), __fsub_rn(__ldg(prow + 1), __ldg(crow + 1)),
-                                  __fsub_rn(__ldg(prow + 2), __ldg(crow + 2))};
+            float rel[3] = {0.f, 0.f, 0.f};
+            if (ce > C) {   // only the half that owns the coordinate columns needs them
+                const float *prow = p.xyz + ((size_t)bi * p.n + k) * 3;
+                const float *crow = p.new_xyz + ((size_t)bi * p.m + (valid ? q : 0)) * 3;
+                rel[0] = __fsub_rn(__ldg(prow), __ldg(crow)); rel[1] = __fsub_rn(__ldg(prow + 1), __ldg(crow + 1));
+                rel[2] = __fsub_rn(__ldg(prow + 2), __ldg(crow + 2));
+            }
             const bool vec = (C & 3) == 0;
-            // feature columns in batches of 32: eight 16-byte loads are issued before the first conversion, so a row costs
-            // ~C/32 L2 round trips instead of C/8
-            int c0 = 0;
+            // feature columns in batches of 32: eight 16-byte loads are issued before the first store, so a row costs
+            // ~C/32 L2 round trips instead of C/8.  Values go to tensor memory as fp32 bits: the tensor core reads the upper
+            // 19 bits (tf32 by truncation), which is what the reference's cuDNN TF32 convolutions feed it as well.
+            int c0 = cs;
             if (vec) {
-                for (; c0 + 32 <= C; c0 += 32) {
+                for (; c0 + 32 <= min(ce, C); c0 += 32) {
                     float4 f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = __ldg(reinterpret_cast<const float4 *>(frow + c0) + j);
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         uint32_t v[8];
-                        v[0] = __float_as_uint(to_tf32(f[2 * h].x)); v[1] = __float_as_uint(to_tf32(f[2 * h].y));
-                        v[2] = __float_as_uint(to_tf32(f[2 * h].z)); v[3] = __float_as_uint(to_tf32(f[2 * h].w));
-                        v[4] = __float_as_uint(to_tf32(f[2 * h + 1].x)); v[5] = __float_as_uint(to_tf32(f[2 * h + 1].y));
-                        v[6] = __float_as_uint(to_tf32(f[2 * h + 1].z)); v[7] = __float_as_uint(to_tf32(f[2 * h + 1].w));
+                        v[0] = __float_as_uint(f[2 * h].x); v[1] = __float_as_uint(f[2 * h].y); v[2] = __float_as_uint(f[2 * h].z); v[3] = __float_as_uint(f[2 * h].w);
+                        v[4] = __float_as_uint(f[2 * h + 1].x); v[5] = __float_as_uint(f[2 * h + 1].y); v[6] = __float_as_uint(f[2 * h + 1].z); v[7] = __float_as_uint(f[2 * h + 1].w);
                         tmem_st8(lane_addr + (uint32_t)(p.col[0] + c0 + 8 * h), v);
                     }
                 }
             }
-            for (; c0 < p.width[0]; c0 += 8) {
+            for (; c0 < ce; c0 += 8) {
                 uint32_t v[8];
                 if (vec && c0 + 8 <= C) {
                     const float4 a = __ldg(reinterpret_cast<const float4 *>(frow + c0));
                     const float4 b2 = __ldg(reinterpret_cast<const float4 *>(frow + c0 + 4));
-                    v[0] = __float_as_uint(to_tf32(a.x)); v[1] = __float_as_uint(to_tf32(a.y)); v[2] = __float_as_uint(to_tf32(a.z)); v[3] = __float_as_uint(to_tf32(a.w));
-                    v[4] = __float_as_uint(to_tf32(b2.x)); v[5] = __float_as_uint(to_tf32(b2.y)); v[6] = __float_as_uint(to_tf32(b2.z)); v[7] = __float_as_uint(to_tf32(b2.w));
+                    v[0] = __float_as_uint(a.x); v[1] = __float_as_uint(a.y); v[2] = __float_as_uint(a.z); v[3] = __float_as_uint(a.w);
+                    v[4] = __float_as_uint(b2.x); v[5] = __float_as_uint(b2.y); v[6] = __float_as_uint(b2.z); v[7] = __float_as_uint(b2.w);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -226,7 +242,7 @@ sa_mlp_kernel(const SaMlpParams p) {
                         float x = 0.f;
                         if (c < C) x = __ldg(frow + c);
                         else if (c < K) x = rel[c - C];
-                        v[j] = __float_as_uint(to_tf32(x));
+                        v[j] = __float_as_uint(x);
                     }
                 }
                 tmem_st8(lane_addr + (uint32_t)(p.col[0] + c0), v);
@@ -255,8 +271,8 @@ sa_mlp_kernel(const SaMlpParams p) {
                 if (!ok) { s_fail = 1; break; }
                 const float *bias = sBias + p.b_off[l];
                 if (l + 1 < p.n_layers) {
-                    // hidden layer: bias + ReLU + tf32 rounding, in place (next layer's A operand)
-                    for (int c0 = 0; c0 < nout; c0 += 16) {
+                    // hidden layer: bias + ReLU in place (next layer's A operand); 16-column chunks alternate between the halves
+                    for (int c0 = half * 16; c0 < nout; c0 += 32) {
                         uint32_t v[16];
                         float bb[16];
                         tmem_ld16(lane_addr + (uint32_t)(p.col[l + 1] + c0), v);
@@ -265,7 +281,7 @@ sa_mlp_kernel(const SaMlpParams p) {
                             *reinterpret_cast<float4 *>(bb + 4 * j) = *reinterpret_cast<const float4 *>(bias + c0 + 4 * j);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f)));
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f));
                         tmem_st16(lane_addr + (uint32_t)(p.col[l + 1] + c0), v);
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -274,7 +290,7 @@ sa_mlp_kernel(const SaMlpParams p) {
                     const bool live = valid && (p.idx_cnt == nullptr || p.idx_cnt[(size_t)bi * p.m + q] > 0);
                     const int seg = p.ns < 32 ? p.ns : 32;                 // lanes of this warp that share a query
                     const bool leader = (lane & (seg - 1)) == 0;
-                    for (int c0 = 0; c0 < nout; c0 += 16) {
+                    for (int c0 = half * 16; c0 < nout; c0 += 32) {
                         uint32_t v[16];
                         float bb[16];
                         tmem_ld16(lane_addr + (uint32_t)(p.col[l + 1] + c0), v);
@@ -306,7 +322,7 @@ sa_mlp_kernel(const SaMlpParams p) {
         __syncthreads();
         if (ok && !s_fail) {
             const int nq = min(SM_QTC, p.m - q0);
-            for (int i = tid; i < c_out * SM_QTC; i += 128) {
+            for (int i = tid; i < c_out * SM_QTC; i += SM_T) {
                 const int c = i / SM_QTC, j = i - c * SM_QTC;
                 if (j < nq) p.out[((size_t)bi * c_out + c) * p.m + q0 + j] = __uint_as_float(sOut[i]);
                 sOut[i] = 0u;
@@ -415,12 +431,15 @@ extern "C" int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, c
     p.b = b; p.n = n; p.m = m; p.ns = nsample; p.c_feat = c_feat;
     p.xyz = xyz; p.new_xyz = new_xyz; p.feats_pm = feats_pm; p.w_packed = packed; p.bias = bias; p.idx = idx; p.idx_cnt = idx_cnt;
     p.out = out; p.status = status;
-    static unsigned long long devs = 0;
-    if (int rc = de6d_ensure_smem(sa_mlp_kernel, 226 * 1024, devs, "sa_mlp smem attribute")) return rc;   // 227 KB minus the static barriers
+    static unsigned long long devs[2] = {0, 0};
+    const bool small = plan.ctas_per_sm >= 3;      // 4 CTAs of 256 threads per SM: <= 64 registers per thread
+    if (int rc = small ? de6d_ensure_smem(sa_mlp_kernel<4>, 226 * 1024, devs[0], "sa_mlp smem attribute")      // 227 KB minus the static barriers
+                       : de6d_ensure_smem(sa_mlp_kernel<2>, 226 * 1024, devs[1], "sa_mlp smem attribute")) return rc;
     const long long n_work = (long long)b * ceil_div(m, SM_QTC);
     long long grid = 148ll * plan.ctas_per_sm;
     if (grid > n_work) grid = n_work;
-    sa_mlp_kernel<<<(unsigned)grid, 128, plan.smem, stream>>>(p);
+    if (small) sa_mlp_kernel<4><<<(unsigned)grid, SM_T, plan.smem, stream>>>(p);
+    else sa_mlp_kernel<2><<<(unsigned)grid, SM_T, plan.smem, stream>>>(p);
     DE6D_CHECK_LAUNCH("sa_mlp_kernel");
     return DE6D_OK;
 }

@@ -2,8 +2,9 @@
 against the reference composition groupers[i] -> mlps[i] -> mask -> max_pool2d of pointnet2_modules.py:461-478.
 
 Two comparisons per shape:
-  * EXACT ARITHMETIC CHECK: a float64 evaluation of the same network whose operands are rounded to tf32 exactly where the
-    kernel rounds them (inputs, BN-folded weights, hidden activations; cvt.rna).  Products of tf32 numbers are exact in
+  * EXACT ARITHMETIC CHECK: a float64 evaluation of the same network whose operands are reduced to tf32 exactly where the
+    kernel / tensor core reduces them (BN-folded weights: cvt.rna when packed; inputs and hidden activations: truncation
+    to the upper 19 bits, what tcgen05.mma kind::tf32 reads).  Products of tf32 numbers are exact in
     fp32 and the kernel accumulates in fp32, so it must agree to fp32 accumulation noise (median error <= 1e-5 of the largest
     activation; single layer: maximum <= 2e-5) plus, in deeper nets, rare tf32 rounding flips of hidden activations (maximum
     <= 5e-4).  This pins the gather, the layer chaining through tensor memory, the mask and the pooling.
@@ -36,6 +37,11 @@ def tf32(x):
     return torch.where(torch.isfinite(x), r, x)
 
 
+def tf32_rz(x):
+    """What the tensor core reads from an fp32 operand: the upper 19 bits (truncation)."""
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
 def make_mlp(widths, seed):
     g = torch.Generator().manual_seed(seed)
     mods = []
@@ -54,11 +60,11 @@ def make_mlp(widths, seed):
 
 def emulate(layers, grouped_kfirst, mask):
     """float64 network on tf32-rounded operands.  grouped_kfirst (B, K, M, ns) fp32 in the reference channel order."""
-    x = tf32(grouped_kfirst).double()
+    x = tf32_rz(grouped_kfirst).double()                                     # activations: truncated by the tensor core
     for li, (w, b) in enumerate(layers):
-        y = torch.einsum("ok,bkms->boms", tf32(w).double(), x) + b.double()[None, :, None, None]
+        y = torch.einsum("ok,bkms->boms", tf32(w).double(), x) + b.double()[None, :, None, None]   # weights: rounded when packed
         y = torch.relu(y.float())          # the kernel adds the bias and applies ReLU in fp32
-        x = tf32(y).double() if li + 1 < len(layers) else y.double()
+        x = tf32_rz(y).double() if li + 1 < len(layers) else y.double()
     x = x * mask[:, None, :, None].double()
     return x.max(dim=3).values.float()
 
