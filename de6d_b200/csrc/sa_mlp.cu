@@ -36,7 +36,8 @@
 namespace de6d {
 
 constexpr int SM_MAX_LAYERS = 4;
-constexpr int SM_QTC = 32;         // queries per work item (output staging: C_out x 32 floats, 128-byte rows)
+constexpr int SM_QTC = 32;         // queries per work item (output staging: C_out x 32 floats, 128-byte rows); 16 when that
+                                   // lets a second CTA fit on the SM
 
 struct SaMlpParams {
     int b, n, m, ns, c_feat;
@@ -47,6 +48,7 @@ struct SaMlpParams {
     int b_off[SM_MAX_LAYERS];          // float offset of layer l's bias
     int w_bytes, bias_floats;
     int tmem_cols;                     // power of two >= 32
+    int qtc;                           // queries per work item (32 or 16)
     int col[SM_MAX_LAYERS + 1];        // TMEM column of the input tile and of each layer's output
     const float *xyz, *new_xyz, *feats_pm, *w_packed, *bias;
     const int *idx, *idx_cnt;
@@ -143,7 +145,7 @@ sa_mlp_kernel(const SaMlpParams p) {
     unsigned char *sW = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
     float *sBias = reinterpret_cast<float *>(sW + p.w_bytes);
     const int c_out = p.width[p.n_layers];
-    uint32_t *sOut = reinterpret_cast<uint32_t *>(sBias + ((p.bias_floats + 31) & ~31));   // [c_out][SM_QTC] float bits (>= 0)
+    uint32_t *sOut = reinterpret_cast<uint32_t *>(sBias + ((p.bias_floats + 31) & ~31));   // [c_out][p.qtc] float bits (>= 0)
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
@@ -156,7 +158,7 @@ sa_mlp_kernel(const SaMlpParams p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     for (int i = tid; i < p.bias_floats; i += SM_T) sBias[i] = p.bias[i];
-    for (int i = tid; i < c_out * SM_QTC; i += SM_T) sOut[i] = 0u;
+    for (int i = tid; i < c_out * p.qtc; i += SM_T) sOut[i] = 0u;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -172,9 +174,9 @@ sa_mlp_kernel(const SaMlpParams p) {
     bool ok = mbar_wait_bounded(&bar_w, 0);
     uint32_t mma_phase = 0;
 
-    const int wpb = (p.m + SM_QTC - 1) / SM_QTC;               // work items per cloud
+    const int wpb = (p.m + p.qtc - 1) / p.qtc;               // work items per cloud
     const int n_work = p.b * wpb;
-    const int tiles = SM_QTC * p.ns / 128;                     // tiles per work item (host guarantees divisibility)
+    const int tiles = p.qtc * p.ns / 128;                     // tiles per work item (host guarantees divisibility)
     const int C = p.c_feat;
     const int K = C + 3;
     // this thread's share of the input columns: [cs, ce), split at a multiple of 32 (or 8 for narrow inputs)
@@ -183,7 +185,7 @@ sa_mlp_kernel(const SaMlpParams p) {
     const int cs = half ? split : 0, ce = half ? W0 : split;
 
     for (int work = blockIdx.x; work < n_work && ok; work += gridDim.x) {
-        const int bi = work / wpb, q0 = (work - bi * wpb) * SM_QTC;
+        const int bi = work / wpb, q0 = (work - bi * wpb) * p.qtc;
         int k_next;
         {
             const int ql0 = row / p.ns, qq = q0 + ql0;
@@ -311,7 +313,7 @@ sa_mlp_kernel(const SaMlpParams p) {
                         }
                         if (leader && valid) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) atomicMax(&sOut[(c0 + j) * SM_QTC + ql], v[j]);
+                            for (int j = 0; j < 16; ++j) atomicMax(&sOut[(c0 + j) * p.qtc + ql], v[j]);
                         }
                     }
                 }
@@ -321,9 +323,9 @@ sa_mlp_kernel(const SaMlpParams p) {
         // ---- write the work item's 32 queries x C_out, re-arm the staging buffer ----
         __syncthreads();
         if (ok && !s_fail) {
-            const int nq = min(SM_QTC, p.m - q0);
-            for (int i = tid; i < c_out * SM_QTC; i += SM_T) {
-                const int c = i / SM_QTC, j = i - c * SM_QTC;
+            const int nq = min(p.qtc, p.m - q0);
+            for (int i = tid; i < c_out * p.qtc; i += SM_T) {
+                const int c = i / p.qtc, j = i - c * p.qtc;
                 if (j < nq) p.out[((size_t)bi * c_out + c) * p.m + q0 + j] = __uint_as_float(sOut[i]);
                 sOut[i] = 0u;
             }
@@ -371,11 +373,14 @@ static int sa_mlp_plan(int n_layers, const int *widths, int ns, SaMlpPlan &plan)
     while (cols < b0 + buf[1]) cols <<= 1;
     p.tmem_cols = cols;
     for (int l = 0; l <= n_layers; ++l) p.col[l] = (l & 1) ? b0 : 0;
-    plan.smem = 1024 + (size_t)p.w_bytes + (size_t)((p.bias_floats + 31) & ~31) * 4 + (size_t)p.width[n_layers] * SM_QTC * 4;
+    const int by_tmem = 512 / cols;
+    auto smem_for = [&](int qtc) { return 1024 + (size_t)p.w_bytes + (size_t)((p.bias_floats + 31) & ~31) * 4 + (size_t)p.width[n_layers] * qtc * 4; };
+    auto ctas_for = [&](int qtc) { return max(1, min(min((int)((226 * 1024) / (smem_for(qtc) + 1024)), by_tmem), 4)); };
+    p.qtc = SM_QTC;
+    if ((16 * ns) % 128 == 0 && ctas_for(16) > ctas_for(SM_QTC)) p.qtc = 16;      // smaller staging buffer buys another CTA per SM
+    plan.smem = smem_for(p.qtc);
     if (plan.smem > 220 * 1024) return -5;                           // weights must stay resident in shared memory
-    int by_smem = (int)((226 * 1024) / (plan.smem + 1024));
-    int by_tmem = 512 / cols;
-    plan.ctas_per_sm = max(1, min(min(by_smem, by_tmem), 4));
+    plan.ctas_per_sm = ctas_for(p.qtc);
     return 0;
 }
 
@@ -435,7 +440,7 @@ extern "C" int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, c
     const bool small = plan.ctas_per_sm >= 3;      // 4 CTAs of 256 threads per SM: <= 64 registers per thread
     if (int rc = small ? de6d_ensure_smem(sa_mlp_kernel<4>, 226 * 1024, devs[0], "sa_mlp smem attribute")      // 227 KB minus the static barriers
                        : de6d_ensure_smem(sa_mlp_kernel<2>, 226 * 1024, devs[1], "sa_mlp smem attribute")) return rc;
-    const long long n_work = (long long)b * ceil_div(m, SM_QTC);
+    const long long n_work = (long long)b * ceil_div(m, p.qtc);
     long long grid = 148ll * plan.ctas_per_sm;
     if (grid > n_work) grid = n_work;
     if (small) sa_mlp_kernel<4><<<(unsigned)grid, SM_T, plan.smem, stream>>>(p);
