@@ -49,6 +49,7 @@ struct SaMlpParams {
     int w_bytes, bias_floats;
     int tmem_cols;                     // power of two >= 32
     int qtc;                           // queries per work item (32 or 16)
+    int pair;                          // 1: two CTAs (cta_group::2) share every layer's weights, half the output rows each
     int col[SM_MAX_LAYERS + 1];        // TMEM column of the input tile and of each layer's output
     const float *xyz, *new_xyz, *feats_pm, *w_packed, *bias;
     const int *idx, *idx_cnt;
@@ -83,6 +84,23 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// cta_group::2 forms: one MMA covers the tiles of BOTH CTAs of a pair (M = 256); each CTA's shared memory holds half of the
+// layer's output rows (the hardware reads B from both), each CTA's tensor memory receives its own 128 rows of D
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {   // arrives on the barrier at this offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__host__ __device__ inline uint32_t umma_idesc_tf32_pair(int n) {     // M = 256 over the pair
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
 // bounded wait (~ seconds): a wrong descriptor must not hang the GPU; returns false on time-out
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
     for (long long it = 0; it < 400000000ll; ++it) {
@@ -114,8 +132,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
 // Packs one layer's BN-folded weights (row-major [n_out x k_in], device) into the tf32-rounded SWIZZLE_128B image the
 // kernel's B descriptors expect.  `xyz_last`: the reference's channel order is (dx, dy, dz, features...) (pointnet2_utils.py:417:
 // cat([grouped_xyz, grouped_features])); the kernel's A tile is (features..., dx, dy, dz, 0-pad), so layer 0's columns are rotated.
-__global__ void sa_mlp_pack_kernel(int n_out, int k_in, int k_pad32, int xyz_last, const float *__restrict__ w, float *__restrict__ image) {
+__global__ void sa_mlp_pack_kernel(int n_out, int k_in, int k_pad32, int xyz_last, int halves, size_t half_stride_bytes,
+                                   const float *__restrict__ w, float *__restrict__ image) {
     const int total = n_out * k_pad32;
+    const int rows_per = n_out / halves;                 // halves = 2: rows [0, n/2) go to CTA 0's image, the rest to CTA 1's
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int r = i / k_pad32, k = i - r * k_pad32;
         float v = 0.f;
@@ -123,7 +143,8 @@ __global__ void sa_mlp_pack_kernel(int n_out, int k_in, int k_pad32, int xyz_las
             const int src = xyz_last ? (k < k_in - 3 ? k + 3 : k - (k_in - 3)) : k;
             v = to_tf32(w[(size_t)r * k_in + src]);
         }
-        *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(image) + sw128_off(n_out, r, k)) = v;
+        const int h = r / rows_per, rl = r - h * rows_per;
+        *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(image) + (size_t)h * half_stride_bytes + sw128_off(rows_per, rl, k)) = v;
     }
 }
 
@@ -132,7 +153,9 @@ __global__ void sa_mlp_pack_kernel(int n_out, int k_in, int k_pad32, int xyz_las
 // CTAs per SM.  MINB = CTAs per SM the register allocation must allow (4 for small nets, 2 for nets that fill tensor memory).
 constexpr int SM_T = 256;
 
-template <int MINB>
+// PAIR: a cluster of two CTAs walks its tiles in lockstep; the leader (cluster rank 0) issues one cta_group::2 MMA per
+// k-step for both tiles, and every block-wide barrier of the single-CTA form becomes a cluster barrier.
+template <int MINB, bool PAIR>
 __global__ void __launch_bounds__(SM_T, MINB)
 sa_mlp_kernel(const SaMlpParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -140,6 +163,9 @@ sa_mlp_kernel(const SaMlpParams p) {
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_fail;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t rank = 0;
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    auto tile_sync = [&]() { if (PAIR) cluster_sync_all(); else __syncthreads(); };
     const int quarter = warp & 3, half = warp >> 2;          // lane quarter of the tile, column half of the work
     const int row = quarter * 32 + lane;                     // this thread's grouped point within a tile
     unsigned char *sW = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
@@ -154,19 +180,25 @@ sa_mlp_kernel(const SaMlpParams p) {
         s_fail = 0;
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     for (int i = tid; i < p.bias_floats; i += SM_T) sBias[i] = p.bias[i];
     for (int i = tid; i < c_out * p.qtc; i += SM_T) sOut[i] = 0u;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    tile_sync();       // PAIR: the peer's barriers exist before the leader's first multicast commit can arrive on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0) {   // all layers' weight images: TMA bulk copies onto one transaction barrier
+    if (tid == 0) {   // all layers' weight images (PAIR: this CTA's half of every layer): TMA bulk copies onto one transaction barrier
+        const unsigned char *wsrc = reinterpret_cast<const unsigned char *>(p.w_packed) + (size_t)rank * p.w_bytes;
         mbar_expect_tx(&bar_w, (uint32_t)p.w_bytes);
         for (int off = 0; off < p.w_bytes; off += 32768) {
             const int len = min(32768, p.w_bytes - off);
-            tma_bulk_g2s(sW + off, reinterpret_cast<const unsigned char *>(p.w_packed) + off, (uint32_t)len, &bar_w);
+            tma_bulk_g2s(sW + off, wsrc + off, (uint32_t)len, &bar_w);
         }
     }
     const uint32_t tbase = tmem_base_s;
@@ -184,7 +216,12 @@ sa_mlp_kernel(const SaMlpParams p) {
     const int split = W0 >= 64 ? ((W0 / 2) & ~31) : ((W0 / 2 + 7) & ~7);
     const int cs = half ? split : 0, ce = half ? W0 : split;
 
-    for (int work = blockIdx.x; work < n_work && ok; work += gridDim.x) {
+    for (int w0 = PAIR ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x; w0 < n_work && (PAIR || ok); w0 += gridDim.x) {
+        // PAIR: the two CTAs take work items w0 and w0 + 1 and must execute the same barriers: a CTA without a work item of
+        // its own recomputes the last one and drops the result; after a time-out nothing is waited for any more
+        int work = PAIR ? w0 + (int)rank : w0;
+        const bool work_valid = work < n_work;
+        if (!work_valid) work = n_work - 1;
         const int bi = work / wpb, q0 = (work - bi * wpb) * p.qtc;
         int k_next;
         {
@@ -255,22 +292,24 @@ sa_mlp_kernel(const SaMlpParams p) {
             for (int l = 0; l < p.n_layers; ++l) {
                 const int kin = p.width[l], nout = p.width[l + 1];
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncthreads();
-                if (tid == 0) {
+                tile_sync();
+                if (tid == 0 && rank == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t idesc = umma_idesc_tf32(nout);
+                    const uint32_t idesc = PAIR ? umma_idesc_tf32_pair(nout) : umma_idesc_tf32(nout);
                     const uint32_t wbase = smem_u32(sW + p.w_off[l]);
                     const uint32_t d_t = tbase + (uint32_t)p.col[l + 1], a_t = tbase + (uint32_t)p.col[l];
+                    const uint32_t brows = (uint32_t)(PAIR ? nout / 2 : nout);      // rows of B held by one CTA
                     for (int ks = 0; ks < kin / 8; ++ks) {
-                        const uint32_t boff = (uint32_t)(ks >> 2) * (uint32_t)nout * 128u + (uint32_t)(ks & 3) * 32u;
-                        umma_ts(d_t, a_t + (uint32_t)ks * 8u, umma_desc_sw128(wbase + boff), idesc, ks > 0);
+                        const uint32_t boff = (uint32_t)(ks >> 2) * brows * 128u + (uint32_t)(ks & 3) * 32u;
+                        if (PAIR) umma_ts_pair(d_t, a_t + (uint32_t)ks * 8u, umma_desc_sw128(wbase + boff), idesc, ks > 0);
+                        else umma_ts(d_t, a_t + (uint32_t)ks * 8u, umma_desc_sw128(wbase + boff), idesc, ks > 0);
                     }
-                    umma_commit(&bar_mma);
+                    if (PAIR) umma_commit_pair(&bar_mma); else umma_commit(&bar_mma);
                 }
-                ok = mbar_wait_bounded(&bar_mma, mma_phase);
+                if (ok) ok = mbar_wait_bounded(&bar_mma, mma_phase);
                 mma_phase ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (!ok) { s_fail = 1; break; }
+                if (!ok) { s_fail = 1; if (!PAIR) break; }
                 const float *bias = sBias + p.b_off[l];
                 if (l + 1 < p.n_layers) {
                     // hidden layer: bias + ReLU in place (next layer's A operand); 16-column chunks alternate between the halves
@@ -318,24 +357,28 @@ sa_mlp_kernel(const SaMlpParams p) {
                     }
                 }
             }
-            if (!ok) break;
+            if (!ok && !PAIR) break;
         }
         // ---- write the work item's 32 queries x C_out, re-arm the staging buffer ----
         __syncthreads();
-        if (ok && !s_fail) {
+        if (ok && !s_fail && work_valid) {
             const int nq = min(p.qtc, p.m - q0);
             for (int i = tid; i < c_out * p.qtc; i += SM_T) {
                 const int c = i / p.qtc, j = i - c * p.qtc;
                 if (j < nq) p.out[((size_t)bi * c_out + c) * p.m + q0 + j] = __uint_as_float(sOut[i]);
-                sOut[i] = 0u;
             }
         }
+        __syncthreads();
+        for (int i = tid; i < c_out * p.qtc; i += SM_T) sOut[i] = 0u;
         __syncthreads();
     }
     if ((!ok || s_fail) && p.status && tid == 0) atomicExch(p.status, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(p.tmem_cols));
+    tile_sync();
+    if (warp == 0) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(p.tmem_cols));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(p.tmem_cols));
+    }
 }
 
 struct SaMlpPlan {
@@ -345,24 +388,27 @@ struct SaMlpPlan {
 };
 
 // widths: [c_in (= 3 + c_feat), c_1, ..., c_L].  Returns 0 and fills `plan`, or a negative reason code.
-static int sa_mlp_plan(int n_layers, const int *widths, int ns, SaMlpPlan &plan) {
+// pair = false: one CTA holds all weights.  pair = true: a cta_group::2 pair, each CTA holds half the output rows of every
+// layer (widths multiples of 32: the 2-CTA MMA with A from tensor memory needs N % 32 == 0).
+static int sa_mlp_plan_one(int n_layers, const int *widths, int ns, bool pair, SaMlpPlan &plan) {
     SaMlpParams &p = plan.p;
     if (n_layers < 1 || n_layers > SM_MAX_LAYERS) return -1;
     if (!(ns == 4 || ns == 8 || ns == 16 || ns == 32 || ns == 64 || ns == 128)) return -2;      // lanes per query must tile 128
     p.n_layers = n_layers;
+    p.pair = pair ? 1 : 0;
     p.width[0] = (widths[0] + 7) & ~7;
     int woff = 0, boff = 0;
     for (int l = 0; l < n_layers; ++l) {
         const int nout = widths[l + 1];
-        if (nout < 16 || nout > 256 || (nout & 15)) return -3;      // A-from-TMEM MMA with M = 128: N % 16 == 0, N <= 256
+        if (nout < 16 || nout > 256 || (nout & (pair ? 31 : 15))) return -3;      // A-from-TMEM MMA: N % 16 == 0 (pair: 32), N <= 256
         p.width[l + 1] = nout;
         p.kblocks[l] = (p.width[l] + 31) / 32;
         p.w_off[l] = woff;
         p.b_off[l] = boff;
-        woff += nout * p.kblocks[l] * 128;                          // multiple of 1024 because nout % 8 == 0
+        woff += (pair ? nout / 2 : nout) * p.kblocks[l] * 128;       // multiple of 1024 because the row count is a multiple of 8
         boff += nout;
     }
-    p.w_bytes = woff;
+    p.w_bytes = woff;                                                // per CTA
     p.bias_floats = boff;
     // TMEM: inputs / outputs alternate between two column buffers
     int buf[2] = {0, 0};
@@ -377,11 +423,16 @@ static int sa_mlp_plan(int n_layers, const int *widths, int ns, SaMlpPlan &plan)
     auto smem_for = [&](int qtc) { return 1024 + (size_t)p.w_bytes + (size_t)((p.bias_floats + 31) & ~31) * 4 + (size_t)p.width[n_layers] * qtc * 4; };
     auto ctas_for = [&](int qtc) { return max(1, min(min((int)((226 * 1024) / (smem_for(qtc) + 1024)), by_tmem), 4)); };
     p.qtc = SM_QTC;
-    if ((16 * ns) % 128 == 0 && ctas_for(16) > ctas_for(SM_QTC)) p.qtc = 16;      // smaller staging buffer buys another CTA per SM
+    if ((16 * ns) % 128 == 0 && (ctas_for(16) > ctas_for(SM_QTC) || smem_for(SM_QTC) > 220 * 1024)) p.qtc = 16;   // smaller staging buffer: another CTA per SM / fits at all
     plan.smem = smem_for(p.qtc);
     if (plan.smem > 220 * 1024) return -5;                           // weights must stay resident in shared memory
-    plan.ctas_per_sm = ctas_for(p.qtc);
+    plan.ctas_per_sm = pair ? 1 : ctas_for(p.qtc);
     return 0;
+}
+static int sa_mlp_plan(int n_layers, const int *widths, int ns, SaMlpPlan &plan) {
+    const int rc = sa_mlp_plan_one(n_layers, widths, ns, false, plan);
+    if (rc != -5) return rc;
+    return sa_mlp_plan_one(n_layers, widths, ns, true, plan) == 0 ? 0 : -5;   // too large for one SM: try a CTA pair
 }
 
 }  // namespace de6d
@@ -397,7 +448,7 @@ extern "C" int de6d_sa_mlp_fits(int n_layers, const int *widths, int nsample) {
 extern "C" size_t de6d_sa_mlp_packed_floats(int n_layers, const int *widths) {
     SaMlpPlan plan;
     if (!widths || sa_mlp_plan(n_layers, widths, 32, plan) != 0) return 0;
-    return (size_t)plan.p.w_bytes / 4;
+    return (size_t)plan.p.w_bytes / 4 * (plan.p.pair ? 2 : 1);
 }
 // weights_cat (device): the layers' BN-folded weight matrices, row-major [c_{l+1} x c_l], concatenated; column order of layer
 // 0 as in the reference's grouped tensor (dx, dy, dz, features...).  packed (device): de6d_sa_mlp_packed_floats floats.
@@ -409,7 +460,8 @@ extern "C" int de6d_sa_mlp_pack(int n_layers, const int *widths, const float *we
     for (int l = 0; l < n_layers; ++l) {
         const int nout = widths[l + 1], kin = widths[l];
         const int kpad = plan.p.kblocks[l] * 32;
-        sa_mlp_pack_kernel<<<ceil_div(nout * kpad, 256), 256, 0, stream>>>(nout, kin, kpad, l == 0 ? 1 : 0, weights_cat + src,
+        sa_mlp_pack_kernel<<<ceil_div(nout * kpad, 256), 256, 0, stream>>>(nout, kin, kpad, l == 0 ? 1 : 0, plan.p.pair ? 2 : 1,
+                                                                           (size_t)plan.p.w_bytes, weights_cat + src,
                                                                            packed + plan.p.w_off[l] / 4);
         DE6D_CHECK_LAUNCH("sa_mlp_pack_kernel");
         src += (size_t)nout * kin;
@@ -436,15 +488,35 @@ extern "C" int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, c
     p.b = b; p.n = n; p.m = m; p.ns = nsample; p.c_feat = c_feat;
     p.xyz = xyz; p.new_xyz = new_xyz; p.feats_pm = feats_pm; p.w_packed = packed; p.bias = bias; p.idx = idx; p.idx_cnt = idx_cnt;
     p.out = out; p.status = status;
-    static unsigned long long devs[2] = {0, 0};
-    const bool small = plan.ctas_per_sm >= 3;      // 4 CTAs of 256 threads per SM: <= 64 registers per thread
-    if (int rc = small ? de6d_ensure_smem(sa_mlp_kernel<4>, 226 * 1024, devs[0], "sa_mlp smem attribute")      // 227 KB minus the static barriers
-                       : de6d_ensure_smem(sa_mlp_kernel<2>, 226 * 1024, devs[1], "sa_mlp smem attribute")) return rc;
+    static unsigned long long devs[3] = {0, 0, 0};
     const long long n_work = (long long)b * ceil_div(m, p.qtc);
+    if (p.pair) {
+        // one cluster of two CTAs per SM pair; the pair takes two work items per pass
+        if (int rc = de6d_ensure_smem(sa_mlp_kernel<1, true>, 226 * 1024, devs[2], "sa_mlp smem attribute")) return rc;
+        long long pairs = (n_work + 1) / 2;
+        if (pairs > 74) pairs = 74;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(SM_T);
+        cfg.dynamicSmemBytes = plan.smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, sa_mlp_kernel<1, true>, p);
+        if (e != cudaSuccess) return de6d_set_cuda_error(e, "sa_mlp_kernel (pair) launch");
+        DE6D_CHECK_LAUNCH("sa_mlp_kernel (pair)");
+        return DE6D_OK;
+    }
+    const bool small = plan.ctas_per_sm >= 3;      // 4 CTAs of 256 threads per SM: <= 64 registers per thread
+    if (int rc = small ? de6d_ensure_smem(sa_mlp_kernel<4, false>, 226 * 1024, devs[0], "sa_mlp smem attribute")      // 227 KB minus the static barriers
+                       : de6d_ensure_smem(sa_mlp_kernel<2, false>, 226 * 1024, devs[1], "sa_mlp smem attribute")) return rc;
     long long grid = 148ll * plan.ctas_per_sm;
     if (grid > n_work) grid = n_work;
-    if (small) sa_mlp_kernel<4><<<(unsigned)grid, SM_T, plan.smem, stream>>>(p);
-    else sa_mlp_kernel<2><<<(unsigned)grid, SM_T, plan.smem, stream>>>(p);
+    if (small) sa_mlp_kernel<4, false><<<(unsigned)grid, SM_T, plan.smem, stream>>>(p);
+    else sa_mlp_kernel<2, false><<<(unsigned)grid, SM_T, plan.smem, stream>>>(p);
     DE6D_CHECK_LAUNCH("sa_mlp_kernel");
     return DE6D_OK;
 }

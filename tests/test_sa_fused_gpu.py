@@ -79,6 +79,10 @@ SHAPES = [
     (2, 512, 64, 8, [3 + 8, 16], 1.5),                        # single layer, 4 queries per warp
     (2, 3000, 500, 32, [3 + 0, 16, 32], 1.0),                 # no features: coordinates only
     (2, 2048, 300, 32, [3 + 5, 16, 32], 1.0),                 # C not a multiple of 4: scalar gather
+    # weights too large for one SM (272 KB / 368 KB in tf32): a cta_group::2 pair holds half of every layer per CTA
+    (2, 1024, 512, 32, [3 + 128, 128, 128, 256], 1.6),
+    (3, 1024, 48, 16, [3 + 128, 128, 192, 256], 2.0),         # 9 work items: the last pair has one idle CTA
+    (1, 2048, 1000, 64, [3 + 128, 128, 128, 256], 2.4),
 ]
 
 
@@ -159,10 +163,12 @@ def test_fused_sa_module_matches_reference_module(lib):
 
 def test_fused_scale_rejects_what_it_cannot_run(lib):
     from de6d_b200 import sa_fused
-    assert not sa_fused.FusedSAScale.supported(make_mlp([131, 128, 128, 256], 0), 32)      # weights > shared memory
+    assert sa_fused.FusedSAScale.supported(make_mlp([131, 128, 128, 256], 0), 32)          # via a CTA pair
+    assert not sa_fused.FusedSAScale.supported(make_mlp([131, 128, 256, 256], 0), 32)      # weights > two SMs' shared memory
+    assert not sa_fused.FusedSAScale.supported(make_mlp([259, 256, 256, 512], 0), 16)      # vote head: > 256 wide
     assert not sa_fused.FusedSAScale.supported(make_mlp([35, 24, 32], 0), 32)              # width not a multiple of 16
     assert not sa_fused.FusedSAScale.supported(make_mlp([35, 32, 32], 0), 24)              # nsample not a power of two
     with pytest.raises(ValueError):
-        sa_fused.FusedSAScale(1.0, 32, make_mlp([131, 128, 128, 256], 0))
+        sa_fused.FusedSAScale(1.0, 32, make_mlp([131, 128, 256, 256], 0))
     train = make_mlp([35, 32], 0).train()
     assert not sa_fused.FusedSAScale.supported(train, 32)
