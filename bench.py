@@ -472,7 +472,8 @@ def sa_mlp_leg(batch, dev):
     """SA layers WITH their shared MLPs -- the reference composition (ball query -> grouped tensor in HBM
     -> cuDNN 1x1 convs + BN + ReLU -> mask -> max-pool; TF32 convolutions, torch's and the reference's default) against the
     fused kernel (ball query -> csrc/sa_mlp.cu: gather + tcgen05 tf32 MLP in tensor memory + mask + max-pool).  Layer shapes:
-    SASA / 3DSSD SA1 and SA2 (the scales whose weights fit in shared memory); random weights, eval-mode BatchNorm."""
+    SASA / 3DSSD SA1, SA2, SA3 (SA3's first two scales run as cta_group::2 pairs, its third -- 131->128->256->256, 464 KB of
+    tf32 weights -- keeps the composition); random weights, eval-mode BatchNorm."""
     import torch
     import torch.nn as nn
     import torch.nn.functional as F
@@ -488,6 +489,7 @@ def sa_mlp_leg(batch, dev):
     layers = {
         "SA1 16384->4096, C=1": (16384, 4096, 1, [(0.2, 32, [16, 16, 32]), (0.4, 32, [16, 16, 32]), (0.8, 64, [32, 32, 64])]),
         "SA2 4096->1024, C=64": (4096, 1024, 64, [(0.4, 32, [64, 64, 128]), (0.8, 32, [64, 64, 128]), (1.6, 64, [64, 96, 128])]),
+        "SA3 1024->512, C=128": (1024, 512, 128, [(1.6, 32, [128, 128, 256]), (3.2, 32, [128, 192, 256]), (4.8, 32, [128, 256, 256])]),
     }
     out = {}
     with torch.cuda.device(dev), torch.no_grad():
@@ -504,23 +506,24 @@ def sa_mlp_leg(batch, dev):
                     flops += 2.0 * a * b * batch * m * ns
                 seq = nn.Sequential(*seq).to(dev).eval()
                 mods.append((r, ns, seq))
-                fused.append(sa_fused.FusedSAScale(r, ns, seq))
-                grouped_bytes += 4 * (c + 3) * batch * m * ns
-            grid = pu.BallQueryGrid(xyz, min(r for r, _, _ in scales))
+                fused.append(sa_fused.FusedSAScale(r, ns, seq) if sa_fused.FusedSAScale.supported(seq, ns) else None)
+                grouped_bytes += 4 * (c + 3) * batch * m * ns * (fused[-1] is not None)
+            grid = pu.BallQueryGrid(xyz, min(r for r, _, _ in scales)) if pu.BallQueryGrid.wanted(n) else None
             _, xyz_t = pu.gather_xyz(xyz, None)
 
-            def unfused():
-                res = []
-                for r, ns, seq in mods:
-                    cnt, idx = pu.ball_query_cnt(r, ns, xyz, new_xyz, grid=grid)
-                    g = pu.group_concat(xyz, new_xyz, feats, idx, xyz_t=xyz_t)
-                    y = seq(g) * (cnt > 0).float().unsqueeze(1).unsqueeze(-1)
-                    res.append(F.max_pool2d(y, kernel_size=[1, ns]).squeeze(-1))
-                return res
+            def one_unfused(r, ns, seq):
+                cnt, idx = pu.ball_query_cnt(r, ns, xyz, new_xyz, grid=grid)
+                g = pu.group_concat(xyz, new_xyz, feats, idx, xyz_t=xyz_t)
+                y = seq(g) * (cnt > 0).float().unsqueeze(1).unsqueeze(-1)
+                return F.max_pool2d(y, kernel_size=[1, ns]).squeeze(-1)
 
-            def fused_run():
+            def unfused():
+                return [one_unfused(r, ns, seq) for r, ns, seq in mods]
+
+            def fused_run():       # scales the kernel cannot take (weights beyond two SMs' shared memory) keep the composition
                 fpm = feats.transpose(1, 2).contiguous()
-                return [fs(xyz, new_xyz, feats, grid=grid, feats_pm=fpm) for fs in fused]
+                return [fs(xyz, new_xyz, feats, grid=grid, feats_pm=fpm) if fs is not None else one_unfused(*md)
+                        for fs, md in zip(fused, mods)]
 
             def timeit(fn, reps=5):
                 for _ in range(2):
@@ -539,7 +542,9 @@ def sa_mlp_leg(batch, dev):
             t_un, t_fu = timeit(unfused), timeit(fused_run)
             out[name] = {"unfused_ms": round(t_un, 3), "fused_ms": round(t_fu, 3), "speedup": round(t_un / t_fu, 2),
                          "mlp_gflop": round(flops / 1e9, 1), "fused_tflops_incl_ball_query": round(flops / (t_fu * 1e-3) / 1e12, 1),
-                         "grouped_tensor_bytes_not_written": grouped_bytes, "max_rel_diff_vs_cudnn_tf32": round(err, 5)}
+                         "grouped_tensor_bytes_not_written": grouped_bytes, "max_rel_diff_vs_cudnn_tf32": round(err, 5),
+                         "scales_fused": ["pair" if (fs is not None and max(fs.widths) > 0 and not sa_fused.FusedSAScale.single_cta(fs)) else
+                                          ("yes" if fs is not None else "no (weights exceed two SMs' shared memory)") for fs in fused]}
             torch.cuda.empty_cache()
     out["tensor_peak_tflops"] = tf32_peak
     out["tensor_peak_source"] = peak_src

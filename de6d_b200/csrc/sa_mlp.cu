@@ -24,9 +24,12 @@
 //            reduces over the nsample lanes of each query (REDUX on the float bits -- the values are >= 0 after ReLU --
 //            or shuffles for nsample < 32, shared-memory atomicMax across warps for nsample > 32);
 //   output   32 queries x C_out are staged in shared memory and written as 128-byte runs of (B, C_out, npoint).
-// Weights of all layers stay resident in shared memory for the lifetime of a persistent CTA (TMA bulk copy once); layers
-// whose weights do not fit (e.g. 131 -> 128 -> 128 -> 256: 272 KB in tf32) are refused (DE6D_ERR_INVALID) and the caller
-// keeps the unfused composition.  TMEM columns are ping-ponged between two buffers (input / output of a layer).
+// Weights of all layers stay resident in shared memory for the lifetime of a persistent CTA (TMA bulk copy once).  MLPs whose
+// tf32 weights exceed one SM's shared memory (131 -> 128 -> 128 -> 256: 272 KB) run as cta_group::2 PAIRS: a cluster of two
+// CTAs walks its tiles in lockstep, each CTA holds half of every layer's output rows, the leader issues one M = 256 MMA per
+// k-step for both tiles (UTCHMMA.2CTA, commit multicast to both CTAs' barriers).  Beyond two SMs' shared memory (or wider than
+// 256 channels) the shape is refused (DE6D_ERR_INVALID) and the caller keeps the unfused composition.  TMEM columns are
+// ping-ponged between two buffers (input / output of a layer).
 //
 // Numerics: tf32 operands (10-bit mantissa; weights rounded to nearest when packed, activations truncated by the tensor core),
 // fp32 accumulation -- the arithmetic of the reference's own
@@ -439,10 +442,12 @@ static int sa_mlp_plan(int n_layers, const int *widths, int ns, SaMlpPlan &plan)
 
 using namespace de6d;
 
-// Can this MLP shape run fused?  widths = [3 + c_feat, c_1, ..., c_L] (host array).  Returns 1 / 0.
+// Can this MLP shape run fused?  widths = [3 + c_feat, c_1, ..., c_L] (host array).  Returns 0 (no), 1 (one CTA holds all
+// weights) or 2 (cta_group::2 pairs: half of every layer's weights per SM).
 extern "C" int de6d_sa_mlp_fits(int n_layers, const int *widths, int nsample) {
     SaMlpPlan plan;
-    return widths && sa_mlp_plan(n_layers, widths, nsample, plan) == 0 ? 1 : 0;
+    if (!widths || sa_mlp_plan(n_layers, widths, nsample, plan) != 0) return 0;
+    return plan.p.pair ? 2 : 1;
 }
 // Floats of the packed weight buffer / of the bias buffer for de6d_sa_mlp_pack and de6d_sa_mlp_fused.
 extern "C" size_t de6d_sa_mlp_packed_floats(int n_layers, const int *widths) {

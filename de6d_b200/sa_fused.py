@@ -68,6 +68,11 @@ class FusedSAScale:
         widths = [layers[0][0].size(1)] + [w.size(0) for w, _ in layers]
         return bool(load().de6d_sa_mlp_fits(len(layers), (C.c_int * len(widths))(*widths), int(nsample)))
 
+    @staticmethod
+    def single_cta(scale: "FusedSAScale") -> bool:
+        """True when one CTA holds all weights; False when the kernel runs as cta_group::2 pairs (half of every layer per SM)."""
+        return scale.mode == 1
+
     def __init__(self, radius: float, nsample: int, mlp: nn.Sequential, radius_in: Optional[float] = None):
         self.radius, self.nsample, self.radius_in = float(radius), int(nsample), radius_in
         layers = fold_mlp(mlp)
@@ -75,7 +80,8 @@ class FusedSAScale:
         self.c_feat = self.widths[0] - 3
         self._w = (C.c_int * len(self.widths))(*self.widths)
         lib = load()
-        if not lib.de6d_sa_mlp_fits(len(layers), self._w, self.nsample):
+        self.mode = int(lib.de6d_sa_mlp_fits(len(layers), self._w, self.nsample))      # 1: one CTA, 2: CTA pairs
+        if not self.mode:
             raise ValueError("shared MLP %s with nsample %d cannot run fused" % (self.widths, self.nsample))
         dev = layers[0][0].device
         cat = torch.cat([w.flatten() for w, _ in layers]).contiguous()

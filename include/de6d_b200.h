@@ -236,7 +236,8 @@ int de6d_points_in_boxes_mask_host(int t, int m, const float *boxes, const float
  * tensor cores (tcgen05.mma kind::tf32, activations in tensor memory), empty-ball mask, max over nsample -- the grouped
  * tensor (b, 3+c, m, nsample) and the hidden activations never reach HBM.
  * widths (HOST int array, n_layers + 1): [3 + c_feat, c_1, ..., c_L]; every c_l a multiple of 16, <= 256; nsample a power
- * of two in 4..128; all layers' tf32 weights must fit in shared memory (de6d_sa_mlp_fits tells).
+ * of two in 4..128; all layers' tf32 weights must fit in one SM's shared memory (de6d_sa_mlp_fits returns 1) or, with widths
+ * that are multiples of 32, in two SMs' (returns 2: the kernel then runs as cta_group::2 pairs); 0 = not supported.
  * de6d_sa_mlp_pack: weights_cat (device) = the layers' BatchNorm-folded matrices, row-major [c_{l+1} x c_l], concatenated,
  * layer 0's columns in the reference order (dx, dy, dz, features...); packed (device) = de6d_sa_mlp_packed_floats floats.
  * de6d_sa_mlp_fused: xyz (b,n,3), new_xyz (b,m,3), feats_pm (b,n,c_feat) POINT-major features (NULL when c_feat == 0),
