@@ -20,6 +20,8 @@ One JSON line on stdout (rank 0):
   cpu_baseline   the oracle (CPU restatement of the reference kernels) on a bounded sample of the same workload
   reference_cuda the same chain issued op by op with the reference's OWN CUDA kernels (oracle/_ref, recompiled for sm_100)
             through the reference's own python, on this GPU -- the yardstick SURVEY.md names; outside every timed region
+  backbone  the reference's own PointNet2FSMSG backbone (SA layers with their MLPs), 16 frames: reference python over the
+            reference kernels / over compat / with fused SA scales;  sa_mlp_fused: SA layers fused vs unfused, 64 frames
   other_configs  BASELINE.json configs[1] (16 frames) and configs[4] (131072-point stress frames), short runs
 oracle/ is used here only for cpu_baseline / reference_cuda / the --impl reference arm, never on the measured GPU path.
 """
@@ -553,6 +555,56 @@ def sa_mlp_leg(batch, dev):
     return out
 
 
+def backbone_leg(batch, dev):
+    """The caller one level above the op chain: the reference's own PointNet2FSMSG backbone (pointnet2_backbone.py:97-263: the
+    three SA layers WITH their shared / aggregation / confidence MLPs) on `batch` 16384-point frames, eval mode:
+      reference_kernels   unmodified reference python over the reference's CUDA extension (oracle/_ref)
+      compat              the same unmodified python over de6d_b200.compat (drop-in: bit-identical outputs)
+      fused               de6d_b200.sa_fused.fuse_backbone (input staging kernel, shared grids, fused SA scales on tcgen05)
+    cuDNN / cuBLAS TF32 allowed as by torch default.  Outside every timed region of the op-chain arm."""
+    import copy
+    import warnings
+    import numpy as np
+    import torch
+    warnings.filterwarnings("ignore")
+    from de6d_b200 import compat, sa_fused, synth
+    from oracle import build_ref, ref_py
+    if not (build_ref.available() and ref_py.available()):
+        return {"unavailable": "oracle/_ref not built"}
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    ours, theirs = ref_py.load_pair()
+    xyz = synth.clouds(batch, 16384, seed=2)
+    inten = np.random.default_rng(2).random((batch, 16384, 1), dtype=np.float32)
+    pts = np.concatenate([np.repeat(np.arange(batch, dtype=np.float32), 16384)[:, None], np.concatenate([xyz, inten], -1).reshape(-1, 4)], 1)
+    out = {}
+    with torch.cuda.device(dev), torch.no_grad():
+        points = torch.from_numpy(pts).to(dev)
+        mods = {}
+        for name, tree in (("reference_kernels", theirs), ("compat", ours)):
+            torch.manual_seed(0)
+            mods[name] = tree.pointnet2_backbone.PointNet2FSMSG(copy.deepcopy(synth.sasa_backbone_cfg()), input_channels=4).to(dev).eval()
+        fused = sa_fused.fuse_backbone(mods["compat"], ffps="fused")
+        runs = {"reference_kernels": lambda: mods["reference_kernels"]({"batch_size": batch, "points": points}),
+                "compat": lambda: mods["compat"]({"batch_size": batch, "points": points}),
+                "fused": lambda: fused({"batch_size": batch, "points": points})}
+        for name, fn in runs.items():
+            fn()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            reps = 2 if name == "reference_kernels" else 5
+            for _ in range(reps):
+                r = fn()
+            torch.cuda.synchronize(dev)
+            ms = 1e3 * (time.perf_counter() - t0) / reps
+            out[name] = {"ms_per_batch": round(ms, 2), "frames_per_s": round(batch / (ms * 1e-3), 1)}
+        a, b = runs["compat"](), runs["reference_kernels"]()
+        out["compat_bit_identical_to_reference"] = bool(torch.equal(a["point_features"], b["point_features"]) and torch.equal(a["point_coords"], b["point_coords"]))
+    out["note"] = ("batch %d, host-synchronised wall clock; SASA / 3DSSD PointNet2FSMSG 16384 -> 4096 -> 1024 -> 512 with d-fps / f-fps+d-fps / "
+                   "s-fps+d-fps sampling, three radius scales per layer; random weights, eval mode" % batch)
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -655,6 +707,11 @@ def run_gpu_arm(args):
             del alt
             torch.cuda.empty_cache()
         line["reference_cuda"] = reference_cuda_leg(cfg, batch, dev, chain)
+        try:
+            line["backbone"] = backbone_leg(16, dev)
+        except Exception as e:  # noqa: BLE001
+            line["backbone"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        torch.cuda.empty_cache()
         try:
             line["sa_mlp_fused"] = sa_mlp_leg(batch, dev)
         except Exception as e:  # noqa: BLE001

@@ -187,3 +187,37 @@ def fuse_sa_module(module: nn.Module, ffps: str = "cdist"):
     forward.fused = [s is not None for s in scales]
     forward.scales = scales
     return forward
+
+
+def fuse_backbone(backbone: nn.Module, ffps: str = "cdist"):
+    """Returns forward(batch_dict) -> batch_dict equivalent to PointNet2FSMSG.forward (pcdet/models/backbones_3d/
+    pointnet2_backbone.py:199-263) of an UNMODIFIED reference backbone in eval mode: input staging with one kernel
+    (de6d_b200.staging.break_up_pc instead of slicing copies + B host-synchronising .sum() calls), every SA module through
+    fuse_sa_module, FP modules (three_nn / three_interpolate + their MLPs) as they are.  Same keys as the reference."""
+    from . import staging
+    if backbone.training:
+        raise ValueError("fuse_backbone needs backbone.eval()")
+    sa = [fuse_sa_module(m, ffps=ffps) for m in backbone.SA_modules]
+
+    @torch.no_grad()
+    def forward(batch_dict):
+        batch_size = batch_dict["batch_size"]
+        batch_idx, xyz, features = staging.break_up_pc(batch_dict["points"], batch_size)
+        l_xyz, l_features, l_scores = [xyz], [features], [None]
+        for i, fwd in enumerate(sa):
+            li_xyz, li_features, li_scores = fwd(l_xyz[i], l_features[i], scores=l_scores[i])
+            l_xyz.append(li_xyz); l_features.append(li_features); l_scores.append(li_scores)
+        batch_dict["point_coords_list"] = [torch.cat([batch_idx[:, :x.size(1)].reshape(-1, 1), x.reshape(-1, 3)], dim=1) for x in l_xyz[1:]]
+        batch_dict["point_scores_list"] = [None if sc is None else sc.reshape(-1, 1) for sc in l_scores[1:]]
+        i = 0
+        if backbone.FP_modules is not None:
+            for i in range(-1, -(len(backbone.FP_modules) + 1), -1):
+                l_features[i - 1] = backbone.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+        point_features = l_features[i - 1].permute(0, 2, 1).contiguous()
+        batch_dict["point_features"] = point_features.view(-1, point_features.shape[-1])
+        batch_dict["point_coords"] = torch.cat((batch_idx[:, :l_xyz[i - 1].size(1)].reshape(-1, 1).float(), l_xyz[i - 1].view(-1, 3)), dim=1)
+        batch_dict["point_scores"] = l_scores[-1]
+        return batch_dict
+
+    forward.fused = [f.fused for f in sa]
+    return forward

@@ -103,3 +103,44 @@ def dist_matrix(xyz, feats=None, gamma=1.0):
         f = np.transpose(feats.astype(np.float64), (0, 2, 1))
         d = d + gamma * np.sqrt(np.maximum(((f[:, :, None, :] - f[:, None, :, :]) ** 2).sum(-1), 0.0))
     return d.astype(np.float32)
+
+
+class AttrDict(dict):
+    """Minimal EasyDict stand-in (attribute access + dict methods) for the reference's `model_cfg` objects."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError:
+            raise AttributeError(k)
+        return v
+
+    @staticmethod
+    def wrap(x):
+        if isinstance(x, dict):
+            return AttrDict({k: AttrDict.wrap(v) for k, v in x.items()})
+        return x
+
+
+def sasa_backbone_cfg(n_points=16384, scale=1):
+    """MODEL.BACKBONE_3D of the SASA / 3DSSD-style PointNet2FSMSG backbone Det6D uses (pointnet2_backbone.py:97-191 reads these
+    keys).  The reference ships no YAML: layer shapes are the ones BASELINE.json configs[1] names
+    (16384 -> 4096 -> 1024 -> 512), radii / nsample / MLP widths as upstream SASA's 3dssd_sasa_car.yaml.  `scale` divides
+    the point counts for small test clouds."""
+    n1, n2, n3 = 4096 // scale, 512 // scale, 256 // scale
+    return AttrDict.wrap({
+        "NAME": "PointNet2FSMSG",
+        "SA_CONFIG": {
+            "NPOINT_LIST": [[n1], [n2, n2], [n3, n3]],
+            "SAMPLE_RANGE_LIST": [[[0, n_points]], [[0, n1], [0, n1]], [[0, n2], [n2, 2 * n2]]],
+            "SAMPLE_METHOD_LIST": [["d-fps"], ["f-fps", "d-fps"], ["s-fps", "d-fps"]],
+            "RADIUS": [[0.2, 0.4, 0.8], [0.4, 0.8, 1.6], [1.6, 3.2, 4.8]],
+            "NSAMPLE": [[32, 32, 64], [32, 32, 64], [32, 32, 32]],
+            "MLPS": [[[16, 16, 32], [16, 16, 32], [32, 32, 64]],
+                     [[64, 64, 128], [64, 64, 128], [64, 96, 128]],
+                     [[128, 128, 256], [128, 192, 256], [128, 256, 256]]],
+            "AGGREGATION_MLPS": [[64], [128], [256]],
+            "CONFIDENCE_MLPS": [[32], [64], []],
+            "WEIGHT_GAMMA": 1.0,
+        },
+    })

@@ -62,7 +62,9 @@ PY_FILES = [
     "pcdet/ops/pointnet2/pointnet2_stack/pointnet2_utils.py",     # imported by pointnet2_modules.py:7
     "pcdet/ops/iou3d_nms/iou3d_nms_utils.py",
     "pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py",
+    "pcdet/ops/pointnet2/pointnet2_stack/pointnet2_modules.py",   # imported by pointnet2_backbone.py:5
     "pcdet/models/model_utils/model_nms_utils.py",
+    "pcdet/models/backbones_3d/pointnet2_backbone.py",            # PointNet2FSMSG: the SASA / 3DSSD / Det6D backbone
     "pcdet/utils/common_utils.py",
     "pcdet/utils/box_utils.py",
 ]

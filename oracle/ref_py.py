@@ -7,7 +7,7 @@ TEST INFRASTRUCTURE ONLY -- imported by tests/ (and by bench.py's `reference_cud
     tree = load_tree("pcdet_ref", extensions=build_ref.load())   # the same files over the reference's own kernels
 
 `tree.pointnet2_utils`, `.pointnet2_modules`, `.iou3d_nms_utils`, `.roiaware_pool3d_utils`, `.model_nms_utils`,
-`.box_utils` are the reference modules.  The package objects are created by hand (types.ModuleType with __path__) so no
+`.box_utils`, `.pointnet2_backbone` are the reference modules.  The package objects are created by hand (types.ModuleType with __path__) so no
 reference __init__.py runs: pcdet/__init__.py needs a generated version.py the mount does not have.
 Third-party imports the mount lacks are stubbed: SharedArray (pcdet/utils/common_utils.py:7) and the out-of-scope
 pointnet2_stack_cuda extension (pointnet2_stack/pointnet2_utils.py:8, imported by pointnet2_modules.py:7 only for the
@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PY_ROOT = os.path.join(HERE, "_ref", "py", "pcdet")
 
 _PACKAGES = ["", "ops", "ops.pointnet2", "ops.pointnet2.pointnet2_batch", "ops.pointnet2.pointnet2_stack",
-             "ops.iou3d_nms", "ops.roiaware_pool3d", "models", "models.model_utils", "utils"]
+             "ops.iou3d_nms", "ops.roiaware_pool3d", "models", "models.model_utils", "models.backbones_3d", "utils"]
 _EXT_PATHS = {
     "pointnet2_batch_cuda": "ops.pointnet2.pointnet2_batch.pointnet2_batch_cuda",
     "iou3d_nms_cuda": "ops.iou3d_nms.iou3d_nms_cuda",
@@ -84,6 +84,7 @@ def load_tree(root="pcdet", extensions=None):
         roiaware_pool3d_utils=imp(root + ".ops.roiaware_pool3d.roiaware_pool3d_utils"),
         model_nms_utils=imp(root + ".models.model_utils.model_nms_utils"),
         box_utils=imp(root + ".utils.box_utils"),
+        pointnet2_backbone=imp(root + ".models.backbones_3d.pointnet2_backbone"),
     )
 
 
