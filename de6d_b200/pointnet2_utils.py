@@ -101,8 +101,12 @@ def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, ga
         fptr, (sb, sn, sc) = None, (0, 0, 0)
     else:
         fptr, (sb, sn, sc) = _strided_features(features, B, N, xyz.device), features.stride()
-    call("de6d_furthest_point_sampling_features_impl", B, N, C, npoint, px, fptr, sb, sn, sc, float(gamma),
-         temp.data_ptr(), out.data_ptr(), int(cluster_size), stream_ptr())
+    if cluster_size:
+        call("de6d_furthest_point_sampling_features_impl", B, N, C, npoint, px, fptr, sb, sn, sc, float(gamma),
+             temp.data_ptr(), out.data_ptr(), int(cluster_size), stream_ptr())
+    else:
+        call("de6d_furthest_point_sampling_features", B, N, C, npoint, px, fptr, sb, sn, sc, float(gamma),
+             temp.data_ptr(), out.data_ptr(), stream_ptr())
     return out
 
 

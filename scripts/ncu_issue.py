@@ -32,6 +32,7 @@ for rep in sys.argv[1:]:
     fps_launches = [d for d in launches if "fps_" in d["Kernel Name"]]
     pos = 0
     for entry, shape in trace:
+        entry = entry.replace("_features_impl", "_features")
         if entry not in want:
             continue
         d = fps_launches[pos]

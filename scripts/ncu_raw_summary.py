@@ -35,7 +35,7 @@ for r in data:
     a["smem"] = val(r, "launch__shared_mem_per_block_dynamic", True) + val(r, "launch__shared_mem_per_block_static", True)
     a["grid"] = int(val(r, "launch__grid_size")); a["block"] = int(val(r, "launch__block_size"))
 tot = sum(a["us"] for a in agg.values())
-print("one chain step, batch 64, eager, single stream, `ncu --set full --clock-control none` (cold-cache, serialised: use the SHARES)")
+print("chain steps (n = launches captured per kernel; the capture spans the warm-up step and the traced step), batch 64, eager, single stream, `ncu --set full --clock-control none` (cold-cache, serialised: use the SHARES)")
 print("%-44s %3s %9s %6s %9s %9s %7s %7s %6s %5s %8s %6s" % ("kernel", "n", "us", "share", "dram rd MB", "dram wr MB", "GB/s", "issue%", "warps%", "regs", "smem KB", "block"))
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
     n = a["n"]

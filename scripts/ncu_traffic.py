@@ -52,6 +52,7 @@ for rep in sys.argv[1:]:
 
     pos = 0
     for entry, shape in trace:
+        entry = entry.replace("_features_impl", "_features")
         names = kernels_of(entry, shape)
         rec = {"kernels": [], "dram_bytes": 0, "dram_read": 0, "dram_write": 0, "ncu_duration_us": 0.0, "report": os.path.basename(rep)}
         for want in names:
