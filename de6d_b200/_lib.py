@@ -24,7 +24,7 @@ PROTOTYPES = {
     "de6d_dist_matrix": [_i, _i, _i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _f, _p, _p],
     "de6d_furthest_point_sampling_features_fits": [_i, _i],
     "de6d_furthest_point_sampling_features": [_i, _i, _i, _i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _f, _p, _p, _p],
-    "de6d_furthest_point_sampling_features_impl": [_i, _i, _i, _i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _f, _p, _p, _i, _p],
+    "de6d_furthest_point_sampling_features_impl": [_i, _i, _i, _i, _p, _p, C.c_longlong, C.c_longlong, C.c_longlong, _f, _p, _p, _i, _i, _p],
     "de6d_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
     "de6d_ball_query": [_i, _i, _i, _f, _i, _p, _p, _p, _p],

@@ -65,48 +65,12 @@ __device__ __forceinline__ void fps_mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ float ord2f(uint32_t u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
-__device__ __forceinline__ uint32_t part1by2(uint32_t x) {  // spread 10 bits to every third bit
-    x &= 0x3ffu;
-    x = (x | (x << 16)) & 0x030000ffu;
-    x = (x | (x << 8)) & 0x0300f00fu;
-    x = (x | (x << 4)) & 0x030c30c3u;
-    x = (x | (x << 2)) & 0x09249249u;
-    return x;
-}
-
-// compact priority for clouds of at most 16384 points: (bit-reversed slot, k / B) in <= 14 bits
-__device__ __forceinline__ uint32_t cprio_of(uint32_t k, int log2B, int ibits) {
-    uint32_t slot = k & ((1u << log2B) - 1u);
-    uint32_t rev = log2B ? (__brev(slot) >> (32 - log2B)) : 0u;
-    return (rev << ibits) | (k >> log2B);
-}
-__device__ __forceinline__ uint32_t index_of_cprio(uint32_t cp, int log2B, int ibits) {
-    uint32_t rev = cp >> ibits;
-    uint32_t slot = log2B ? (__brev(rev) >> (32 - log2B)) : 0u;
-    return ((cp & ((1u << ibits) - 1u)) << log2B) | slot;
-}
-
 // S-FPS key: reference evaluates d * max(w, 1e-12) in double and rounds once to float
 // (sampling_gpu.cu:465; 1e-12 is a double literal).  For w >= 1e-12f the double product of two floats is
 // exact, so one float multiply gives the same rounding; only smaller weights take the double path.
 __device__ __forceinline__ float sfps_key(float d, float w) {
     if (w >= 1e-11f) return __fmul_rn(d, w);
     return (float)((double)d * fmax((double)w, 1e-12));
-}
-
-// Lower bound of sqdist(p, q) over every p inside the box: per axis the gap g = max(lo-q, q-hi, 0) satisfies
-// |fl(p-q)| >= g (rounding is monotone), and fl(dy*dy), fl(dx*dx+t), fl(dz*dz+t) are monotone in |d.| and t,
-// so the value below never exceeds the distance the kernel would compute for any point of the bucket.
-__device__ __forceinline__ float bucket_lower_bound(float lox, float hix, float loy, float hiy, float loz, float hiz,
-                                                    float qx, float qy, float qz) {
-    float gx = fmaxf(fmaxf(__fsub_rn(lox, qx), __fsub_rn(qx, hix)), 0.f);
-    float gy = fmaxf(fmaxf(__fsub_rn(loy, qy), __fsub_rn(qy, hiy)), 0.f);
-    float gz = fmaxf(fmaxf(__fsub_rn(loz, qz), __fsub_rn(qz, hiz)), 0.f);
-    return __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
 }
 
 // CL = true: the cloud is split over the CTAs of a thread-block cluster, CAP points each (n_in up to 8 * 16384).  Every

@@ -82,12 +82,13 @@ def furthest_point_sample_matrix(matrix: torch.Tensor, npoint: int) -> torch.Ten
 
 @torch.no_grad()
 def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, gamma: float, npoint: int,
-                                   cluster_size: int = 0) -> torch.Tensor:
+                                   cluster_size: int = 0, prune: int = 0) -> torch.Tensor:
     """F-FPS without the (B, N, N) matrix: identical indices to
         furthest_point_sample_matrix(calc_dist_matrix_for_sampling(xyz, features, gamma), npoint)
     (the reference's call pair, pointnet2_modules.py:383-388).  xyz (B, N, 3), features (B, N, C) with any strides.
     One thread-block cluster (6 or 8 CTAs) per cloud evaluates only the selected rows out of distributed shared memory; shapes that do not
-    fit on chip take the two-call form.  cluster_size: 0 = automatic, 6 / 8 pin the cluster size (tests, tuning)."""
+    fit on chip take the two-call form.  cluster_size: 0 = automatic, 6 / 8 pin the cluster size; prune: 0 = automatic, 1 = dense
+    kernel, 2 = pruned kernel (64-point buckets skipped when their bounding box proves nothing can change) -- tests, tuning."""
     from ._lib import call, load
     from .compat._common import stream_ptr
     B, N, _ = xyz.shape
@@ -101,9 +102,9 @@ def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, ga
         fptr, (sb, sn, sc) = None, (0, 0, 0)
     else:
         fptr, (sb, sn, sc) = _strided_features(features, B, N, xyz.device), features.stride()
-    if cluster_size:
+    if cluster_size or prune:
         call("de6d_furthest_point_sampling_features_impl", B, N, C, npoint, px, fptr, sb, sn, sc, float(gamma),
-             temp.data_ptr(), out.data_ptr(), int(cluster_size), stream_ptr())
+             temp.data_ptr(), out.data_ptr(), int(cluster_size), int(prune), stream_ptr())
     else:
         call("de6d_furthest_point_sampling_features", B, N, C, npoint, px, fptr, sb, sn, sc, float(gamma),
              temp.data_ptr(), out.data_ptr(), stream_ptr())

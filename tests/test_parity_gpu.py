@@ -275,9 +275,83 @@ def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
     x, f = cu(xyz), cu(feats).permute(0, 2, 1)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
     for s in (6, 8):
-        assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s), two), "cluster size %d" % s
+        for pr in (1, 2):   # dense / pruned kernel
+            assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s, prune=pr), two), "cluster size %d, prune %d" % (s, pr)
     big = pu.furthest_point_sample_features(x.repeat(6, 1, 1), f.repeat(6, 1, 1), 1.0, M)   # 18 clouds: the launcher's own pick
     assert torch.equal(big[:3], two) and torch.equal(big[15:], two)
+
+
+@pytest.mark.parametrize("B,N,C,M,gamma,cloud", [(2, 4096, 64, 512, 1.0, "uniform"), (2, 4096, 64, 512, 1.0, "lidar"), (2, 4096, 64, 4096, 0.05, "lidar"),
+                                                   (2, 4096, 64, 300, 30.0, "uniform"), (3, 384, 8, 96, 0.7, "uniform"), (2, 1000, 16, 1000, 1.0, "lidar"),
+                                                   (1, 700, 0, 50, 1.0, "uniform"), (2, 2048, 7, 33, 1.0, "uniform"), (2, 3000, 32, 100, 0.0, "uniform"),
+                                                   (1, 8192, 16, 64, 1.0, "lidar"), (1, 65, 3, 65, 1.0, "uniform"), (2, 5000, 40, 200, 1.0, "uniform"),
+                                                   (1, 130, 128, 100, 1.0, "uniform")])
+def test_fused_ffps_pruned_equals_dense(ops, B, N, C, M, gamma, cloud):
+    """The pruned cluster kernel (Morton-sorted 64-point buckets, a warp skips its bucket when the bounding box proves that no
+    min-distance can change) picks the indices of the dense kernel and of the two-call path and leaves the same running
+    min-distances: coordinate-dominated metrics (most buckets skipped), feature-dominated ones (none skipped), gamma = 0,
+    exhaustive sampling, duplicated points, ragged last buckets, no features at all."""
+    pu = ops[0]
+    from de6d_b200._lib import call
+    from de6d_b200.compat._common import stream_ptr
+    xyz = (synth.lidar_clouds if cloud == "lidar" else synth.clouds)(B, N, seed=N + C)
+    xyz[:, 5] = xyz[:, 2]
+    feats = synth.features(B, max(C, 1), N, seed=C)
+    feats[:, :, 5] = feats[:, :, 2]
+    x = cu(xyz)
+    f = cu(feats).permute(0, 2, 1) if C else None
+    two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, gamma), M)
+    outs = {}
+    for pr in (1, 2):
+        for s in (6, 8):
+            out = torch.empty(B, M, dtype=torch.int32, device="cuda")
+            temp = torch.full((B, N), 1e10, device="cuda")
+            fp, (sb, sn, sc) = (f.data_ptr(), f.stride()) if C else (None, (0, 0, 0))
+            try:
+                call("de6d_furthest_point_sampling_features_impl", B, N, C, M, x.data_ptr(), fp, sb, sn, sc, float(gamma),
+                     temp.data_ptr(), out.data_ptr(), s, pr, stream_ptr())
+            except RuntimeError as e:          # a (shape, cluster size) pair one of the kernels does not cover
+                assert "not covered" in str(e) or "does not fit" in str(e), e
+                continue
+            outs[(pr, s)] = (out, temp)
+            assert torch.equal(out, two), "prune %d cluster %d" % (pr, s)
+    assert any(pr == 2 for pr, _ in outs), "the pruned kernel covered no cluster size"
+    temps = [t for _, t in outs.values()]
+    for t in temps[1:]:
+        assert torch.equal(t, temps[0])
+
+
+@pytest.mark.parametrize("kind", ["nan_xyz", "inf_xyz", "nan_feat", "neg_gamma", "nan_temp"])
+def test_fused_ffps_pruned_non_finite(ops, kind):
+    """Inputs that switch the bound off (non-finite coordinates, NaN min-distances, negative gamma) or poison single
+    distances (NaN features): pruned == dense, bit for bit."""
+    pu = ops[0]
+    from de6d_b200._lib import call
+    from de6d_b200.compat._common import stream_ptr
+    B, N, C, M = 2, 4096, 64, 200
+    xyz = synth.clouds(B, N, seed=21)
+    feats = synth.features(B, C, N, seed=21)
+    gamma = 1.0
+    if kind == "nan_xyz":
+        xyz[0, 100, 1] = np.nan
+    elif kind == "inf_xyz":
+        xyz[1, 7, 0] = np.inf
+    elif kind == "nan_feat":
+        feats[0, 3, 50] = np.nan
+    elif kind == "neg_gamma":
+        gamma = -0.5
+    x, f = cu(xyz), cu(feats).permute(0, 2, 1)
+    res = []
+    for pr in (1, 2):
+        out = torch.empty(B, M, dtype=torch.int32, device="cuda")
+        temp = torch.full((B, N), 1e10, device="cuda")
+        if kind == "nan_temp":
+            temp[0, 9] = float("nan")
+        call("de6d_furthest_point_sampling_features_impl", B, N, C, M, x.data_ptr(), f.data_ptr(), *f.stride(), float(gamma),
+             temp.data_ptr(), out.data_ptr(), 0, pr, stream_ptr())
+        res.append((out, temp))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1].nan_to_num(nan=-7.0), res[1][1].nan_to_num(nan=-7.0))
 
 
 def test_fused_ffps_full_batch(ops):
