@@ -174,9 +174,89 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         }
         prune = (misc[1] == 0);
         const float inv = ext > 0.f ? 1023.0f / ext : 0.f;
+        __syncthreads();  // red[] fully consumed before the sort buffers (aliasing only sx/sy/sz, but keep phases apart)
+        // Stable LSD radix sort (6-bit digits, 5 passes over the 30-bit Morton code) where its buffers fit under the
+        // coordinate arrays: the same order as sorting (code << 32 | index), i.e. the same buckets, for ~1/10 of the
+        // shared-memory traffic of the bitonic network below (105 passes over 16384 8-byte items took 60 % of the
+        // prologue, 0.25 ms of a 2.6 ms launch).  Warp w ranks the items at positions [w * 32 * BPW, (w + 1) * 32 * BPW):
+        // per 32 items one match.any gives the rank among equal digits inside the warp, hist[digit][warp] the count in
+        // the warp's earlier items; an exclusive scan over (digit, warp) turns the counts into stable global offsets.
+        constexpr bool USE_RADIX = (2 * CAP >= 260 * NW + 64) && CAP <= 16384;
+        if constexpr (USE_RADIX) {
+            uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);                    // [CAP] Morton code of point k
+            unsigned short *ia = reinterpret_cast<unsigned short *>(keys + CAP);        // [CAP] point at position p (ping)
+            unsigned short *ib = ia + CAP;                                              // [CAP] (pong)
+            unsigned short *loff = ib + CAP;                                            // [CAP] rank of position p inside (digit, warp)
+            uint32_t *hist = reinterpret_cast<uint32_t *>(loff + CAP);                  // [64][NW]
+            uint32_t *wtot = hist + 64 * NW;                                            // [NW]
+            for (int k = tid; k < n; k += T) {
+                uint32_t key = 0;
+                if (prune) {
+                    uint32_t qx = (uint32_t)fminf(fmaxf((xyz[k * 3 + 0] - lo[0]) * inv, 0.f), 1023.f);
+                    uint32_t qy = (uint32_t)fminf(fmaxf((xyz[k * 3 + 1] - lo[1]) * inv, 0.f), 1023.f);
+                    uint32_t qz = (uint32_t)fminf(fmaxf((xyz[k * 3 + 2] - lo[2]) * inv, 0.f), 1023.f);
+                    key = part1by2(qx) | (part1by2(qy) << 1) | (part1by2(qz) << 2);
+                }
+                keys[k] = key;
+                ia[k] = (unsigned short)k;
+            }
+            const uint32_t lt_mask = (1u << lane) - 1u;
+            if (prune) {
+                for (int sh = 0; sh < 30; sh += 6) {
+                    __syncthreads();
+                    hist[2 * tid] = 0u; hist[2 * tid + 1] = 0u;     // 64 * NW == 2 * T
+                    __syncthreads();
+#pragma unroll 4
+                    for (int i = 0; i < BPW; ++i) {
+                        const int pos = ((w * BPW + i) << 5) | lane;
+                        const bool a = pos < n;
+                        const uint32_t d = a ? ((keys[ia[a ? pos : 0]] >> sh) & 63u) : (64u + (uint32_t)lane);
+                        const uint32_t mm = __match_any_sync(0xffffffffu, d);
+                        const uint32_t rank = __popc(mm & lt_mask);
+                        const uint32_t cnt = a ? hist[d * NW + w] : 0u;
+                        __syncwarp();
+                        if (a && rank == 0u) hist[d * NW + w] = cnt + (uint32_t)__popc(mm);
+                        __syncwarp();
+                        if (a) loff[pos] = (unsigned short)(cnt + rank);
+                    }
+                    __syncthreads();
+                    {   // exclusive scan over hist[0 .. 64 * NW), two entries per thread
+                        const uint32_t e0 = hist[2 * tid], e1 = hist[2 * tid + 1];
+                        uint32_t inc = e0 + e1;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= o) inc += t;
+                        }
+                        if (lane == 31) wtot[w] = inc;
+                        __syncthreads();
+                        uint32_t base = 0u;
+                        for (int i = 0; i < w; ++i) base += wtot[i];
+                        const uint32_t ex = base + inc - (e0 + e1);
+                        hist[2 * tid] = ex; hist[2 * tid + 1] = ex + e0;
+                    }
+                    __syncthreads();
+#pragma unroll 4
+                    for (int i = 0; i < BPW; ++i) {
+                        const int pos = ((w * BPW + i) << 5) | lane;
+                        if (pos < n) {
+                            const unsigned short k = ia[pos];
+                            const uint32_t d = (keys[k] >> sh) & 63u;
+                            ib[hist[d * NW + w] + loff[pos]] = k;
+                        }
+                    }
+                    unsigned short *t = ia; ia = ib; ib = t;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < BPW; ++j) {
+                int p = ((j * NW + w) << 5) | lane;
+                kk[j] = p < n ? (uint32_t)ia[p] : 0xffffffffu;
+            }
+        } else {
         int np = 64;
         while (np < n) np <<= 1;
-        __syncthreads();  // red[] fully consumed before sortbuf (aliasing only sx/sy, but keep phases apart)
         for (int k = tid; k < np; k += T) {
             unsigned long long item = ~0ull;
             if (k < n) {
@@ -208,6 +288,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         for (int j = 0; j < BPW; ++j) {
             int p = ((j * NW + w) << 5) | lane;
             kk[j] = p < n ? (uint32_t)sortbuf[p] : 0xffffffffu;
+        }
         }
         __syncthreads();  // every item read before the coordinates overwrite the sort buffer
     } else {
@@ -364,38 +445,14 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                 act = prune ? (lb < bmaxt) : (((lane * NW + w) << 5) < n);
             }
             unsigned mask = __ballot_sync(0xffffffffu, act);
-            auto visit = [&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                if constexpr (j < BPW) {
-                    const int p = ((j * NW + w) << 5) | lane;
-                    constexpr uint32_t off = (uint32_t)j * NW * 32u * 4u;
-                    const float x = lds_f32(sx_s + lane_off + off), y = lds_f32(sy_s + lane_off + off), z = lds_f32(sz_s + lane_off + off);
-                    unsigned short cps;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cps) : "r"(scp_s + (lane_off >> 1) + (off >> 1)));
-                    float t = fminf(sqdist(x, y, z, qx[0], qy[0], qz[0]), temp[j]);
-#pragma unroll
-                    for (int i = 1; i < SPECK; ++i)
-                        if (i < na) t = fminf(sqdist(x, y, z, qx[i], qy[i], qz[i]), t);
-                    if (p >= n) t = -INFINITY;
-                    temp[j] = t;
-                    const uint32_t v_own = (p < n && t == t) ? f2ord(t) : 0u;
-                    const uint32_t wd_own = ((uint32_t)cps << 14) | (uint32_t)p;
-                    // bucket maximum, its owner (smallest word among the lanes at the maximum) and the second-best value.
-                    // The second-best is the maximum again when two lanes tie, else the best value below it: both
-                    // REDUX after the first depend on the maximum only, so they overlap instead of forming a chain.
-                    const uint32_t v = __reduce_max_sync(0xffffffffu, v_own);
-                    const bool top = v_own == v;
-                    const uint32_t wd = __reduce_min_sync(0xffffffffu, top ? wd_own : 0xffffffffu);
-                    const uint32_t below = __reduce_max_sync(0xffffffffu, top ? 0u : v_own);
-                    const uint32_t sec = __popc(__ballot_sync(0xffffffffu, top)) > 1 ? v : below;
-                    if (lane == j) { bval = v; bword = wd; bmaxt = v ? ord2f(v) : -INFINITY; bval2 = sec; }
-                }
-            };
-            while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
+            // Visit the active buckets two at a time.  Only the access to the bucket's min-distance register needs the bucket
+            // number as a compile-time constant, so the warp-uniform switch holds just `t = min(d, temp[j]); temp[j] = t`;
+            // the coordinate loads, the distances to the pending samples and the bucket statistics run on runtime addresses
+            // outside it, and the loads / REDUX chains of the two buckets overlap.
+            auto touch = [&](int j, float d) -> float {
+                float t = d;
                 switch (j) {
-#define DE6D_FPS_CASE(J) case J: visit(std::integral_constant<int, J>{}); break;
+#define DE6D_FPS_CASE(J) case J: if constexpr (J < BPW) { t = fminf(d, temp[J < BPW ? J : 0]); temp[J < BPW ? J : 0] = t; } break;
                     DE6D_FPS_CASE(0) DE6D_FPS_CASE(1) DE6D_FPS_CASE(2) DE6D_FPS_CASE(3) DE6D_FPS_CASE(4) DE6D_FPS_CASE(5)
                     DE6D_FPS_CASE(6) DE6D_FPS_CASE(7) DE6D_FPS_CASE(8) DE6D_FPS_CASE(9) DE6D_FPS_CASE(10) DE6D_FPS_CASE(11)
                     DE6D_FPS_CASE(12) DE6D_FPS_CASE(13) DE6D_FPS_CASE(14) DE6D_FPS_CASE(15) DE6D_FPS_CASE(16) DE6D_FPS_CASE(17)
@@ -405,6 +462,50 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
 #undef DE6D_FPS_CASE
                     default: break;
                 }
+                return t;
+            };
+            while (mask) {
+                const int j0 = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const bool two = mask != 0u;
+                const int j1 = two ? __ffs(mask) - 1 : j0;
+                mask &= mask - 1;   // no-op on 0
+                const uint32_t off0 = (uint32_t)j0 * (NW * 32u * 4u), off1 = (uint32_t)j1 * (NW * 32u * 4u);
+                const float x0 = lds_f32(sx_s + lane_off + off0), y0 = lds_f32(sy_s + lane_off + off0), z0 = lds_f32(sz_s + lane_off + off0);
+                const float x1 = lds_f32(sx_s + lane_off + off1), y1 = lds_f32(sy_s + lane_off + off1), z1 = lds_f32(sz_s + lane_off + off1);
+                unsigned short cps0, cps1;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cps0) : "r"(scp_s + (lane_off >> 1) + (off0 >> 1)));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cps1) : "r"(scp_s + (lane_off >> 1) + (off1 >> 1)));
+                // distances to the pending samples: the running minimum over them first, then against the stored min-distance
+                // (fminf keeps the non-NaN operand, so the result is the same set minimum as folding them one by one)
+                float d0 = sqdist(x0, y0, z0, qx[0], qy[0], qz[0]), d1 = sqdist(x1, y1, z1, qx[0], qy[0], qz[0]);
+#pragma unroll
+                for (int i = 1; i < SPECK; ++i)
+                    if (i < na) {
+                        d0 = fminf(sqdist(x0, y0, z0, qx[i], qy[i], qz[i]), d0);
+                        d1 = fminf(sqdist(x1, y1, z1, qx[i], qy[i], qz[i]), d1);
+                    }
+                const float t0 = touch(j0, d0);
+                float t1 = t0;
+                if (two) t1 = touch(j1, d1);
+                const int p0 = ((j0 * NW + w) << 5) | lane, p1 = ((j1 * NW + w) << 5) | lane;
+                // padding slots (p >= n) hold -inf from the start and min() keeps it there
+                const uint32_t v_own0 = (p0 < n && t0 == t0) ? f2ord(t0) : 0u, v_own1 = (p1 < n && t1 == t1) ? f2ord(t1) : 0u;
+                const uint32_t wd_own0 = ((uint32_t)cps0 << 14) | (uint32_t)p0, wd_own1 = ((uint32_t)cps1 << 14) | (uint32_t)p1;
+                // bucket maximum, its owner (smallest word among the lanes at the maximum) and the second-best value.
+                // The second-best is the maximum again when two lanes tie, else the best value below it: both
+                // REDUX after the first depend on the maximum only, so they overlap instead of forming a chain.
+                const uint32_t v0 = __reduce_max_sync(0xffffffffu, v_own0);
+                const uint32_t v1 = __reduce_max_sync(0xffffffffu, v_own1);
+                const bool top0 = v_own0 == v0, top1 = v_own1 == v1;
+                const uint32_t wd0 = __reduce_min_sync(0xffffffffu, top0 ? wd_own0 : 0xffffffffu);
+                const uint32_t wd1 = __reduce_min_sync(0xffffffffu, top1 ? wd_own1 : 0xffffffffu);
+                const uint32_t below0 = __reduce_max_sync(0xffffffffu, top0 ? 0u : v_own0);
+                const uint32_t below1 = __reduce_max_sync(0xffffffffu, top1 ? 0u : v_own1);
+                const uint32_t sec0 = __popc(__ballot_sync(0xffffffffu, top0)) > 1 ? v0 : below0;
+                const uint32_t sec1 = __popc(__ballot_sync(0xffffffffu, top1)) > 1 ? v1 : below1;
+                if (lane == j0) { bval = v0; bword = wd0; bmaxt = v0 ? ord2f(v0) : -INFINITY; bval2 = sec0; }
+                if (two && lane == j1) { bval = v1; bword = wd1; bmaxt = v1 ? ord2f(v1) : -INFINITY; bval2 = sec1; }
             }
         };
         const uint32_t wq_s = (uint32_t)__cvta_generic_to_shared(wq), bq_s = (uint32_t)__cvta_generic_to_shared(bq);
@@ -801,6 +902,9 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, const float *w, f
         return launch_bucket<MODE, 32, 16, true>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
     }
     if constexpr (MODE == FPS_D) {
+        // tuning: up to 6 / 8 samples per round at 16384 points (impl 7 / 8)
+        if (n > 4096 && n <= 16384 && log2B + ibits <= 14 && impl == 7) return launch_bucket<MODE, 16, 32, true, 6>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
+        if (n > 4096 && n <= 16384 && log2B + ibits <= 14 && impl == 8) return launch_bucket<MODE, 16, 32, true, 8>(b, n, m, log2B, ibits, xyz, w, temp, idx, s);
         // default D-FPS of large clouds: pruned buckets + up to 4 samples per barrier round (measured 4-10 % faster at
         // 16384 points: 3.8 samples per round, but the per-sample instruction work, not the barrier count, bounds the
         // kernel; at <= 4096 points the one-sample rounds are as fast).  impl 5 forces it at any size (tests).

@@ -71,7 +71,7 @@ int de6d_furthest_point_sampling_features(int b, int n, int c, int m, const floa
                                           long long stride_b, long long stride_n, long long stride_c, float gamma,
                                           float *temp, int *idx, cudaStream_t stream);
 /* The same with the thread-block cluster size pinned (0 = automatic, 6 or 8) and the kernel form pinned (prune: 0 =
- * automatic, 1 = dense: every distance of every selected row, 2 = pruned: a warp skips its 64-point bucket when the
+ * automatic (dense wherever it fits: measured faster), 1 = dense: every distance of every selected row, 2 = pruned: a warp skips its 64-point bucket when the
  * bucket's bounding box proves that no running min-distance can change; an error if the shape is not covered).
  * Identical results in every combination -- tests and tuning. */
 int de6d_furthest_point_sampling_features_impl(int b, int n, int c, int m, const float *xyz, const float *features,

@@ -103,7 +103,7 @@ def test_dfps_cluster_stress_shape(lib):
 
 
 @pytest.mark.parametrize("N,M,kind", [(16384, 4096, "uniform"), (16384, 4096, "lidar"), (4096, 4096, "dup"), (3000, 1500, "grid"),
-                                      (512, 512, "uniform"), (16384, 600, "clusters")])
+                                      (512, 512, "uniform"), (16384, 600, "clusters"), (16384, 5000, "dup"), (12000, 3000, "grid16")])
 def test_dfps_multi_sample_rounds_exact(orc, lib, N, M, kind):
     """The default D-FPS kernel takes up to 4 samples per barrier round (speculation that is only accepted when it
     provably equals the sequential choice).  Stress the acceptance logic: exhaustive sampling (M == N: rounds where
@@ -120,11 +120,14 @@ def test_dfps_multi_sample_rounds_exact(orc, lib, N, M, kind):
     elif kind == "grid":
         g = np.stack(np.meshgrid(np.arange(15), np.arange(20), np.arange(10), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
         xyz = np.stack([g[rng.permutation(N)] * np.float32(0.5), g[rng.permutation(N)] * np.float32(0.25)])
+    elif kind == "grid16":
+        g = np.stack(np.meshgrid(np.arange(30), np.arange(40), np.arange(10), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+        xyz = np.stack([g[rng.permutation(N)] * np.float32(0.5), g[rng.permutation(N)] * np.float32(0.25)])
     else:
         centres = rng.uniform(0, 50, (12, 3))
         xyz = (centres[rng.integers(0, 12, (2, N))] + rng.normal(0, 0.05, (2, N, 3))).astype(np.float32)
     want, wtemp = orc.furthest_point_sample(xyz, M, return_temp=True)
-    for impl in (0, 4, 5):     # automatic, one sample per round, multi-sample rounds forced at every size
+    for impl in (0, 4, 5, 7, 8):     # automatic, one sample per round, multi-sample rounds forced at every size, 6 / 8 samples per round
         idx, temp = _fps_impl(xyz, M, impl)
         np.testing.assert_array_equal(idx, want)
         np.testing.assert_array_equal(temp, wtemp)
