@@ -60,6 +60,7 @@ PROTOTYPES = {
     "de6d_sa_mlp_packed_floats": [_i, _p],
     "de6d_sa_mlp_pack": [_i, _p, _p, _p, _p],
     "de6d_sa_mlp_fused": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
+    "de6d_sa_mlp_fused_slice": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _p, _p],
     "de6d_stage_points": [_i, _i, _i, _i, C.c_longlong, _p, _p, _p, _p, _p, _p, _p],
     "de6d_last_error_string": [],
     "de6d_version": [],

@@ -88,6 +88,10 @@ __device__ __forceinline__ float sfps_key(float d, float w) {
 // its bucket's maximum or behind a warp's two reported maxima could out-rank a candidate, so every bucket also
 // caches its second-best value and every warp reports the largest value it did not report: a candidate is only
 // accepted if it is strictly above that bound.  On FPS workloads ~3.5 of 4 candidates are accepted per round.
+#ifdef DE6D_FPS_STATS   // tuning builds only (scripts/micro/fps_stats.py): rounds, accepted samples, why a round stopped
+__device__ unsigned long long de6d_fps_stats_dev[8];
+#endif
+
 template <int MODE, int NW, int BPW, bool PRUNE, bool CL = false, int SPECK = 1>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict__ xyz_all,
@@ -510,6 +514,9 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         };
         const uint32_t wq_s = (uint32_t)__cvta_generic_to_shared(wq), bq_s = (uint32_t)__cvta_generic_to_shared(bq);
         int it = first_it;
+#ifdef DE6D_FPS_STATS
+        unsigned long long st_rounds = 0, st_acc = 0, st_bound = 0, st_pair = 0, st_limit = 0, st_zero = 0, st_full = 0;
+#endif
         while (it < m) {
             update_pass(A);
             // ---- this warp's two best bucket maxima + the largest value it does not report ----
@@ -551,6 +558,13 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                 bool go = true;
 #pragma unroll
                 for (int j = 1; j < SPECK; ++j) {
+#ifdef DE6D_FPS_STATS
+                    if (go) {
+                        if (!(j < limit)) ++st_limit;
+                        else if (!(cv[j] > bound)) ++st_bound;
+                        else if (!(ord2f(cv[j]) > 0.f)) ++st_zero;
+                    }
+#endif
                     if (go && j < limit && cv[j] > bound && ord2f(cv[j]) > 0.f) {
                         const uint32_t pj = cw[j] & 0x3fffu;
                         const float cx = lds_f32(sx_s + pj * 4u), cy = lds_f32(sy_s + pj * 4u), cz = lds_f32(sz_s + pj * 4u);
@@ -560,6 +574,9 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                         for (int i = 0; i < j; ++i) ok = ok && !(sqdist(cx, cy, cz, qx[i], qy[i], qz[i]) < tj);
                         if (ok) { qx[j] = cx; qy[j] = cy; qz[j] = cz; A = j + 1; }
                         else go = false;
+#ifdef DE6D_FPS_STATS
+                        if (!ok) ++st_pair;
+#endif
                     } else {
                         go = false;
                     }
@@ -575,7 +592,17 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                 if (tid == 0) idxs[it] = 0;
             }
             it += A;
+#ifdef DE6D_FPS_STATS
+            ++st_rounds; st_acc += A; if (A == SPECK) ++st_full;
+#endif
         }
+#ifdef DE6D_FPS_STATS
+        if (tid == 0) {
+            atomicAdd(&de6d_fps_stats_dev[0], st_rounds); atomicAdd(&de6d_fps_stats_dev[1], st_acc); atomicAdd(&de6d_fps_stats_dev[2], st_bound);
+            atomicAdd(&de6d_fps_stats_dev[3], st_pair); atomicAdd(&de6d_fps_stats_dev[4], st_limit); atomicAdd(&de6d_fps_stats_dev[5], st_zero);
+            atomicAdd(&de6d_fps_stats_dev[6], st_full);
+        }
+#endif
         // the reference applies every sample's update except the last one's: catch up on the final round
         if (A > 1) update_pass(A - 1);
     } else {
@@ -974,3 +1001,15 @@ extern "C" int de6d_furthest_point_sampling_matrix(int b, int n, int m, const fl
     DE6D_CHECK_LAUNCH("fps_matrix_kernel");
     return DE6D_OK;
 }
+
+#ifdef DE6D_FPS_STATS
+extern "C" int de6d_fps_stats_read(unsigned long long *out8, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out8, de6d::de6d_fps_stats_dev, 8 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(de6d::de6d_fps_stats_dev, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif

@@ -57,6 +57,7 @@ struct SaMlpParams {
     const float *xyz, *new_xyz, *feats_pm, *w_packed, *bias;
     const int *idx, *idx_cnt;
     float *out;
+    int out_c_total, out_c_off;        // out is (b, out_c_total, m); this launch writes channels [out_c_off, out_c_off + width[n_layers])
     int *status;                       // optional debug word (bounded waits), may be null
 };
 
@@ -368,7 +369,7 @@ sa_mlp_kernel(const SaMlpParams p) {
             const int nq = min(p.qtc, p.m - q0);
             for (int i = tid; i < c_out * p.qtc; i += SM_T) {
                 const int c = i / p.qtc, j = i - c * p.qtc;
-                if (j < nq) p.out[((size_t)bi * c_out + c) * p.m + q0 + j] = __uint_as_float(sOut[i]);
+                if (j < nq) p.out[((size_t)bi * p.out_c_total + p.out_c_off + c) * p.m + q0 + j] = __uint_as_float(sOut[i]);
             }
         }
         __syncthreads();
@@ -476,9 +477,24 @@ extern "C" int de6d_sa_mlp_pack(int n_layers, const int *widths, const float *we
 
 // xyz (b,n,3), new_xyz (b,m,3), feats_pm (b,n,c_feat) POINT-major (NULL when c_feat == 0), idx (b,m,nsample), idx_cnt (b,m) or
 // NULL (no empty-ball mask), packed / bias from de6d_sa_mlp_pack (bias: concatenated folded BN biases), out (b, c_L, m).
+// ..._slice: out is (b, out_channels, m) and this launch fills channels [out_channel_offset, out_channel_offset + c_L) of it.
+// A last layer too wide for the shared memory of an SM pair is run as several launches over row blocks of its weight
+// matrix (each launch recomputes the earlier layers: de6d_b200/sa_fused.py decides), e.g. 131 -> 128 -> 256 -> {128 | 128}.
+extern "C" int de6d_sa_mlp_fused_slice(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
+                                       const float *feats_pm, const int *idx, const int *idx_cnt, int n_layers, const int *widths,
+                                       const float *packed, const float *bias, float *out, int out_channels, int out_channel_offset,
+                                       int *status, cudaStream_t stream);
 extern "C" int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
                                  const float *feats_pm, const int *idx, const int *idx_cnt, int n_layers, const int *widths,
                                  const float *packed, const float *bias, float *out, int *status, cudaStream_t stream) {
+    if (!widths || n_layers < 1 || n_layers > SM_MAX_LAYERS) return de6d_set_error(DE6D_ERR_INVALID, "sa_mlp_fused: widths / n_layers");
+    return de6d_sa_mlp_fused_slice(b, n, m, nsample, c_feat, xyz, new_xyz, feats_pm, idx, idx_cnt, n_layers, widths, packed, bias, out,
+                                   widths[n_layers], 0, status, stream);
+}
+extern "C" int de6d_sa_mlp_fused_slice(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
+                                       const float *feats_pm, const int *idx, const int *idx_cnt, int n_layers, const int *widths,
+                                       const float *packed, const float *bias, float *out, int out_channels, int out_channel_offset,
+                                       int *status, cudaStream_t stream) {
     if (b < 0 || n < 0 || m < 0 || nsample < 0 || c_feat < 0) return de6d_set_error(DE6D_ERR_INVALID, "sa_mlp_fused: negative size");
     if (b == 0 || m == 0) return DE6D_OK;
     if (!xyz || !new_xyz || !idx || !widths || !packed || !bias || !out || (c_feat > 0 && !feats_pm) || n == 0)
@@ -493,6 +509,9 @@ extern "C" int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, c
     p.b = b; p.n = n; p.m = m; p.ns = nsample; p.c_feat = c_feat;
     p.xyz = xyz; p.new_xyz = new_xyz; p.feats_pm = feats_pm; p.w_packed = packed; p.bias = bias; p.idx = idx; p.idx_cnt = idx_cnt;
     p.out = out; p.status = status;
+    if (out_channel_offset < 0 || out_channel_offset + widths[n_layers] > out_channels)
+        return de6d_set_error(DE6D_ERR_INVALID, "sa_mlp_fused_slice: channel slice outside the output");
+    p.out_c_total = out_channels; p.out_c_off = out_channel_offset;
     static unsigned long long devs[3] = {0, 0, 0};
     const long long n_work = (long long)b * ceil_div(m, p.qtc);
     if (p.pair) {

@@ -60,13 +60,28 @@ class FusedSAScale:
     """
 
     @staticmethod
+    def plan(widths, nsample: int):
+        """(mode, parts): mode 1 = one CTA holds all weights, 2 = cta_group::2 pairs, 0 = cannot run fused; parts = how many
+        row blocks the LAST layer is split into (one launch each, every launch recomputing the earlier layers) -- 1 unless the
+        whole MLP exceeds the shared memory of an SM pair (SASA SA3's 131 -> 128 -> 256 -> 256: two blocks of 128 rows)."""
+        lib = load()
+        for parts in (1, 2, 4):
+            if widths[-1] % parts:
+                break
+            w = list(widths[:-1]) + [widths[-1] // parts]
+            mode = int(lib.de6d_sa_mlp_fits(len(w) - 1, (C.c_int * len(w))(*w), int(nsample)))
+            if mode:
+                return mode, parts
+        return 0, 0
+
+    @staticmethod
     def supported(mlp: nn.Sequential, nsample: int) -> bool:
         try:
             layers = fold_mlp(mlp)
         except ValueError:
             return False
         widths = [layers[0][0].size(1)] + [w.size(0) for w, _ in layers]
-        return bool(load().de6d_sa_mlp_fits(len(layers), (C.c_int * len(widths))(*widths), int(nsample)))
+        return bool(FusedSAScale.plan(widths, nsample)[0])
 
     @staticmethod
     def single_cta(scale: "FusedSAScale") -> bool:
@@ -78,17 +93,23 @@ class FusedSAScale:
         layers = fold_mlp(mlp)
         self.widths = [layers[0][0].size(1)] + [w.size(0) for w, _ in layers]
         self.c_feat = self.widths[0] - 3
-        self._w = (C.c_int * len(self.widths))(*self.widths)
         lib = load()
-        self.mode = int(lib.de6d_sa_mlp_fits(len(layers), self._w, self.nsample))      # 1: one CTA, 2: CTA pairs
+        self.mode, self.parts = self.plan(self.widths, self.nsample)      # mode 1: one CTA, 2: CTA pairs; parts: launches over the last layer
         if not self.mode:
             raise ValueError("shared MLP %s with nsample %d cannot run fused" % (self.widths, self.nsample))
         dev = layers[0][0].device
-        cat = torch.cat([w.flatten() for w, _ in layers]).contiguous()
-        self.bias = torch.cat([b for _, b in layers]).contiguous()
-        self.packed = torch.empty(int(lib.de6d_sa_mlp_packed_floats(len(layers), self._w)), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            call("de6d_sa_mlp_pack", len(layers), self._w, cat.data_ptr(), self.packed.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        rows = self.widths[-1] // self.parts
+        self._w = (C.c_int * len(self.widths))(*(self.widths[:-1] + [rows]))
+        self.slices = []      # (packed weights, biases, first output channel) per launch
+        for h in range(self.parts):
+            last_w, last_b = layers[-1][0][h * rows:(h + 1) * rows], layers[-1][1][h * rows:(h + 1) * rows]
+            cat = torch.cat([w.flatten() for w, _ in layers[:-1]] + [last_w.flatten()]).contiguous()
+            bias = torch.cat([b for _, b in layers[:-1]] + [last_b]).contiguous()
+            packed = torch.empty(int(lib.de6d_sa_mlp_packed_floats(len(layers), self._w)), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                call("de6d_sa_mlp_pack", len(layers), self._w, cat.data_ptr(), packed.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            self.slices.append((packed, bias, h * rows))
+        self.packed, self.bias = self.slices[0][0], self.slices[0][1]
         self.n_layers = len(layers)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
 
@@ -99,12 +120,14 @@ class FusedSAScale:
         M = new_xyz.size(1)
         out = torch.empty((B, self.widths[-1], M), dtype=torch.float32, device=xyz.device)
         chk = pu._chk
-        call("de6d_sa_mlp_fused", B, N, M, self.nsample, self.c_feat, chk(xyz, "xyz", torch.float32, (B, N, 3)),
-             chk(new_xyz, "new_xyz", torch.float32, (B, M, 3)),
-             None if self.c_feat == 0 else chk(feats_pm, "feats_pm", torch.float32, (B, N, self.c_feat)),
-             chk(idx, "idx", torch.int32, (B, M, self.nsample)), None if idx_cnt is None else chk(idx_cnt, "idx_cnt", torch.int32, (B, M)),
-             self.n_layers, self._w, self.packed.data_ptr(), self.bias.data_ptr(), out.data_ptr(), self.status.data_ptr(),
-             torch.cuda.current_stream().cuda_stream)
+        px, pn = chk(xyz, "xyz", torch.float32, (B, N, 3)), chk(new_xyz, "new_xyz", torch.float32, (B, M, 3))
+        pf = None if self.c_feat == 0 else chk(feats_pm, "feats_pm", torch.float32, (B, N, self.c_feat))
+        pi = chk(idx, "idx", torch.int32, (B, M, self.nsample))
+        pc = None if idx_cnt is None else chk(idx_cnt, "idx_cnt", torch.int32, (B, M))
+        for packed, bias, c_off in self.slices:
+            call("de6d_sa_mlp_fused_slice", B, N, M, self.nsample, self.c_feat, px, pn, pf, pi, pc, self.n_layers, self._w,
+                 packed.data_ptr(), bias.data_ptr(), out.data_ptr(), self.widths[-1], c_off, self.status.data_ptr(),
+                 torch.cuda.current_stream().cuda_stream)
         return out
 
     @torch.no_grad()

@@ -252,6 +252,13 @@ int de6d_sa_mlp_pack(int n_layers, const int *widths, const float *weights_cat, 
 int de6d_sa_mlp_fused(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
                       const float *feats_pm, const int *idx, const int *idx_cnt, int n_layers, const int *widths,
                       const float *packed, const float *bias, float *out, int *status, cudaStream_t stream);
+/* The same, writing channels [out_channel_offset, out_channel_offset + c_L) of an out tensor (b, out_channels, m): an MLP whose
+ * LAST layer is too wide for the shared memory of an SM pair (131 -> 128 -> 256 -> 256: 464 KB of tf32 weights) runs as several
+ * launches over row blocks of the last layer's weight matrix, each with its own packed image (widths[n_layers] = rows of the block). */
+int de6d_sa_mlp_fused_slice(int b, int n, int m, int nsample, int c_feat, const float *xyz, const float *new_xyz,
+                            const float *feats_pm, const int *idx, const int *idx_cnt, int n_layers, const int *widths,
+                            const float *packed, const float *bias, float *out, int out_channels, int out_channel_offset,
+                            int *status, cudaStream_t stream);
 
 /* ---- next to the path: full-pose boxes -------------------------------------------------- */
 

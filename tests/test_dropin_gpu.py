@@ -363,7 +363,7 @@ def test_fused_backbone_matches_reference_backbone(pair):
     from de6d_b200 import sa_fused, synth
     a, _ = _backbone_pair(pair, cfg_scale=4)
     fwd = sa_fused.fuse_backbone(a)
-    assert fwd.fused == [[True, True, True], [True, True, True], [True, True, False]]
+    assert fwd.fused == [[True, True, True], [True, True, True], [True, True, True]]   # SA3's 131->128->256->256 as two launches over the last layer
     B, N = 2, 4096
     xyz = synth.clouds(B, N, seed=9) * np.float32(0.3)
     inten = np.random.default_rng(9).random((B, N, 1), dtype=np.float32)

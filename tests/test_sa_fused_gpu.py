@@ -83,6 +83,9 @@ SHAPES = [
     (2, 1024, 512, 32, [3 + 128, 128, 128, 256], 1.6),
     (3, 1024, 48, 16, [3 + 128, 128, 192, 256], 2.0),         # 9 work items: the last pair has one idle CTA
     (1, 2048, 1000, 64, [3 + 128, 128, 128, 256], 2.4),
+    # weights beyond two SMs' shared memory (464 KB): two launches over 128-row blocks of the last layer, each a CTA pair
+    (2, 1024, 512, 32, [3 + 128, 128, 256, 256], 4.8),
+    (2, 1024, 100, 16, [3 + 64, 128, 256, 256], 2.0),
 ]
 
 
@@ -148,7 +151,8 @@ def test_fused_sa_module_matches_reference_module(lib):
                 mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5); mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.2)
     m.eval()
     fwd = sa_fused.fuse_sa_module(m)
-    assert fwd.fused == [True, True, False]                                      # 67->128->256->256 does not fit in shared memory
+    assert fwd.fused == [True, True, True]                                       # 67->128->256->256: the last layer in two 128-row launches
+    assert [sc.parts for sc in fwd.scales] == [1, 1, 2]
     B, N = 3, 1024
     xyz = cu(synth.clouds(B, N, seed=5) * np.float32(0.2))
     feats = torch.randn(B, 64, N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
@@ -164,11 +168,12 @@ def test_fused_sa_module_matches_reference_module(lib):
 def test_fused_scale_rejects_what_it_cannot_run(lib):
     from de6d_b200 import sa_fused
     assert sa_fused.FusedSAScale.supported(make_mlp([131, 128, 128, 256], 0), 32)          # via a CTA pair
-    assert not sa_fused.FusedSAScale.supported(make_mlp([131, 128, 256, 256], 0), 32)      # weights > two SMs' shared memory
+    assert sa_fused.FusedSAScale.supported(make_mlp([131, 128, 256, 256], 0), 32)          # weights > two SMs' shared memory: last layer split
+    assert sa_fused.FusedSAScale.plan([131, 128, 256, 256], 32) == (2, 2)
     assert not sa_fused.FusedSAScale.supported(make_mlp([259, 256, 256, 512], 0), 16)      # vote head: > 256 wide
     assert not sa_fused.FusedSAScale.supported(make_mlp([35, 24, 32], 0), 32)              # width not a multiple of 16
     assert not sa_fused.FusedSAScale.supported(make_mlp([35, 32, 32], 0), 24)              # nsample not a power of two
     with pytest.raises(ValueError):
-        sa_fused.FusedSAScale(1.0, 32, make_mlp([131, 128, 256, 256], 0))
+        sa_fused.FusedSAScale(1.0, 32, make_mlp([259, 256, 256, 512], 0))
     train = make_mlp([35, 32], 0).train()
     assert not sa_fused.FusedSAScale.supported(train, 32)
