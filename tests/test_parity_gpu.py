@@ -259,11 +259,14 @@ def test_fused_ffps_adversarial_ties(ops, C, M, kind):
     x, f = cu(xyz), cu(feats).permute(0, 2, 1)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
     assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M), two)
+    if C == 64:
+        for s in (4, 6, 8):
+            assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s), two), "cluster size %d" % s
 
 
 @pytest.mark.parametrize("N,kind", [(4096, "dup"), (4096, "equal_features"), (3600, "plain"), (4224, "plain"), (4100, "dup")])
 def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
-    """The 6-CTA (704 points per CTA, uneven last slice) and 8-CTA cluster forms of the fused F-FPS kernel pick the same
+    """The 4-CTA (1024 points per CTA, half of the channels read from shared memory), 6-CTA (704 points per CTA, uneven last slice) and 8-CTA cluster forms of the fused F-FPS kernel pick the same
     indices as the two-call path, ties included (the launcher chooses between them by batch size; forced here)."""
     pu = ops[0]
     B, C, M = 3, 64, 1024 if kind == "dup" else 300
@@ -277,8 +280,10 @@ def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
         feats[:] = 1.0
     x, f = cu(xyz), cu(feats).permute(0, 2, 1)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
-    for s in (6, 8):
+    for s in (4, 6, 8):
         for pr in (1, 2):   # dense / pruned kernel
+            if s == 4 and (pr == 2 or N > 4096):      # 4-CTA clusters: dense kernel, at most 4 x 1024 points
+                continue
             assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s, prune=pr), two), "cluster size %d, prune %d" % (s, pr)
     big = pu.furthest_point_sample_features(x.repeat(6, 1, 1), f.repeat(6, 1, 1), 1.0, M)   # 18 clouds: the launcher's own pick
     assert torch.equal(big[:3], two) and torch.equal(big[15:], two)
