@@ -390,19 +390,28 @@ bq_grid_query_kernel(int n, int m, float r_abs, float r2_in, float r2_out, int n
                     const int s = __ldg(cell_start + row + ix0), e = __ldg(cell_start + row + ix1 + 1);
                     seen += e - s;
                     if (seen > cand_limit) { serial = true; break; }
-                    for (int i = s; i < e; ++i) {
-                        const float4 p = __ldg(sorted + i);
-                        const int k = __float_as_int(p.w);
-                        if (k > last) continue;   // list is full and this index cannot enter it
-                        const float d2 = sqdist(qx, qy, qz, p.x, p.y, p.z);
-                        bool hit = d2 < r2_out;
-                        if (MODE == BQ_DILATED) hit = hit && (d2 >= r2_in);
-                        if (!hit) continue;
-                        int pos = (L < nsample) ? L : nsample - 1;   // full: the current largest drops out
-                        while (pos > 0 && list[pos - 1] > k) { list[pos] = list[pos - 1]; --pos; }
-                        list[pos] = k;
-                        if (L < nsample) ++L;
-                        if (L == nsample) last = list[nsample - 1];
+                    // candidates four at a time: the 16-byte records are random L2 reads and the test -> insert chain behind
+                    // each of them is short, so one load in flight per thread left the kernel waiting on L2 latency
+                    for (int i = s; i < e; i += 4) {
+                        float4 pc[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pc[j] = __ldg(sorted + min(i + j, e - 1));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (i + j >= e) break;
+                            const float4 p = pc[j];
+                            const int k = __float_as_int(p.w);
+                            if (k > last) continue;   // list is full and this index cannot enter it
+                            const float d2 = sqdist(qx, qy, qz, p.x, p.y, p.z);
+                            bool hit = d2 < r2_out;
+                            if (MODE == BQ_DILATED) hit = hit && (d2 >= r2_in);
+                            if (!hit) continue;
+                            int pos = (L < nsample) ? L : nsample - 1;   // full: the current largest drops out
+                            while (pos > 0 && list[pos - 1] > k) { list[pos] = list[pos - 1]; --pos; }
+                            list[pos] = k;
+                            if (L < nsample) ++L;
+                            if (L == nsample) last = list[nsample - 1];
+                        }
                     }
                 }
             }
