@@ -88,7 +88,8 @@ def furthest_point_sample_features(xyz: torch.Tensor, features: torch.Tensor, ga
     (the reference's call pair, pointnet2_modules.py:383-388).  xyz (B, N, 3), features (B, N, C) with any strides.
     One thread-block cluster (6 or 8 CTAs) per cloud evaluates only the selected rows out of distributed shared memory; shapes that do not
     fit on chip take the two-call form.  cluster_size: 0 = automatic, 6 / 8 pin the cluster size; prune: 0 = automatic, 1 = dense
-    kernel, 2 = pruned kernel (64-point buckets skipped when their bounding box proves nothing can change) -- tests, tuning."""
+    kernel, 2 = pruned kernel (64-point buckets skipped when their bounding box proves nothing can change), 3 = pruned kernel with the
+    remaining buckets evaluated by the whole CTA -- tests, tuning."""
     from ._lib import call, load
     from .compat._common import stream_ptr
     B, N, _ = xyz.shape

@@ -70,9 +70,10 @@ int de6d_furthest_point_sampling_features_fits(int n, int c);
 int de6d_furthest_point_sampling_features(int b, int n, int c, int m, const float *xyz, const float *features,
                                           long long stride_b, long long stride_n, long long stride_c, float gamma,
                                           float *temp, int *idx, cudaStream_t stream);
-/* The same with the thread-block cluster size pinned (0 = automatic, 6 or 8) and the kernel form pinned (prune: 0 =
+/* The same with the thread-block cluster size pinned (0 = automatic, 4, 6 or 8) and the kernel form pinned (prune: 0 =
  * automatic (dense wherever it fits: measured faster), 1 = dense: every distance of every selected row, 2 = pruned: a warp skips its 64-point bucket when the
- * bucket's bounding box proves that no running min-distance can change; an error if the shape is not covered).
+ * bucket's bounding box proves that no running min-distance can change; 3 = the same with the surviving buckets evaluated by the
+ * whole CTA; an error if the shape is not covered).  cluster_size 4 (64 channels, 3073..4096 points) applies to the dense form.
  * Identical results in every combination -- tests and tuning. */
 int de6d_furthest_point_sampling_features_impl(int b, int n, int c, int m, const float *xyz, const float *features,
                                                long long stride_b, long long stride_n, long long stride_c, float gamma,

@@ -281,8 +281,8 @@ def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
     x, f = cu(xyz), cu(feats).permute(0, 2, 1)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
     for s in (4, 6, 8):
-        for pr in (1, 2):   # dense / pruned kernel
-            if s == 4 and (pr == 2 or N > 4096):      # 4-CTA clusters: dense kernel, at most 4 x 1024 points
+        for pr in (1, 2, 3):   # dense / pruned / pruned with cooperative evaluation
+            if s == 4 and (pr >= 2 or N > 4096):      # 4-CTA clusters: dense kernel, at most 4 x 1024 points
                 continue
             assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s, prune=pr), two), "cluster size %d, prune %d" % (s, pr)
     big = pu.furthest_point_sample_features(x.repeat(6, 1, 1), f.repeat(6, 1, 1), 1.0, M)   # 18 clouds: the launcher's own pick
@@ -310,7 +310,7 @@ def test_fused_ffps_pruned_equals_dense(ops, B, N, C, M, gamma, cloud):
     f = cu(feats).permute(0, 2, 1) if C else None
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, gamma), M)
     outs = {}
-    for pr in (1, 2):
+    for pr in (1, 2, 3):
         for s in (6, 8):
             out = torch.empty(B, M, dtype=torch.int32, device="cuda")
             temp = torch.full((B, N), 1e10, device="cuda")
@@ -323,7 +323,7 @@ def test_fused_ffps_pruned_equals_dense(ops, B, N, C, M, gamma, cloud):
                 continue
             outs[(pr, s)] = (out, temp)
             assert torch.equal(out, two), "prune %d cluster %d" % (pr, s)
-    assert any(pr == 2 for pr, _ in outs), "the pruned kernel covered no cluster size"
+    assert any(pr == 2 for pr, _ in outs) and any(pr == 3 for pr, _ in outs), "the pruned kernel covered no cluster size"
     temps = [t for _, t in outs.values()]
     for t in temps[1:]:
         assert torch.equal(t, temps[0])
@@ -350,7 +350,7 @@ def test_fused_ffps_pruned_non_finite(ops, kind):
         gamma = -0.5
     x, f = cu(xyz), cu(feats).permute(0, 2, 1)
     res = []
-    for pr in (1, 2):
+    for pr in (1, 2, 3):
         out = torch.empty(B, M, dtype=torch.int32, device="cuda")
         temp = torch.full((B, N), 1e10, device="cuda")
         if kind == "nan_temp":
@@ -358,8 +358,9 @@ def test_fused_ffps_pruned_non_finite(ops, kind):
         call("de6d_furthest_point_sampling_features_impl", B, N, C, M, x.data_ptr(), f.data_ptr(), *f.stride(), float(gamma),
              temp.data_ptr(), out.data_ptr(), 0, pr, stream_ptr())
         res.append((out, temp))
-    assert torch.equal(res[0][0], res[1][0])
-    assert torch.equal(res[0][1].nan_to_num(nan=-7.0), res[1][1].nan_to_num(nan=-7.0))
+    for r in res[1:]:
+        assert torch.equal(res[0][0], r[0])
+        assert torch.equal(res[0][1].nan_to_num(nan=-7.0), r[1].nan_to_num(nan=-7.0))
 
 
 def test_fused_ffps_full_batch(ops):
