@@ -5,13 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from de6d_b200 import synth, pointnet2_utils as pu
 
-B = 16
+B = 32
 big = torch.from_numpy(synth.clouds(B, 16384, 0)).cuda()
 sub = pu.furthest_point_sample(big, 4096).long()
 xyz = torch.gather(big, 1, sub[..., None].expand(-1, -1, 3)).contiguous()
-for fscale in (1.0, 0.1, 3.0):
+for fscale in (1.0,):
     f = (torch.from_numpy(synth.features(B, 64, 4096, 10)).cuda() * fscale).permute(0, 2, 1)
-    for prune, S in ((1, 4), (1, 6), (3, 6), (3, 8)):
+    for prune, S in ((1, 4), (1, 44), (1, 6)):
         line = []
         for m in (1, 2, 65, 129, 257, 512):
             fn = lambda: pu.furthest_point_sample_features(xyz, f, 1.0, m, cluster_size=S, prune=prune)

@@ -21,7 +21,7 @@ def timeit(fn, n=10):
 
 rows = []
 for cloud in ("uniform", "lidar"):
-    for B in (16, 64):
+    for B in (32, 64):
         gen = synth.lidar_clouds if cloud == "lidar" else synth.clouds
         big = torch.from_numpy(gen(B, 16384, 0)).cuda()
         sub = pu.furthest_point_sample(big, 4096).long()
@@ -29,7 +29,7 @@ for cloud in ("uniform", "lidar"):
         for fscale in (1.0,):
             f = (torch.from_numpy(synth.features(B, 64, 4096, 10)).cuda() * fscale).permute(0, 2, 1)
             ref = None
-            for prune, S in ((1, 4), (1, 6), (3, 6), (3, 8), (0, 0)):
+            for prune, S in ((1, 4), (1, 44), (1, 6), (0, 0)):
                 out = pu.furthest_point_sample_features(xyz, f, 1.0, 512, cluster_size=S, prune=prune)
                 ref = out if ref is None else ref
                 assert torch.equal(out, ref)

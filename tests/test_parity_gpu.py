@@ -260,7 +260,7 @@ def test_fused_ffps_adversarial_ties(ops, C, M, kind):
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
     assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M), two)
     if C == 64:
-        for s in (4, 6, 8):
+        for s in (4, 44, 6, 8):
             assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s), two), "cluster size %d" % s
 
 
@@ -280,9 +280,9 @@ def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
         feats[:] = 1.0
     x, f = cu(xyz), cu(feats).permute(0, 2, 1)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
-    for s in (4, 6, 8):
+    for s in (4, 44, 6, 8):    # 44: 4-CTA clusters with four points per thread
         for pr in (1, 2, 3):   # dense / pruned / pruned with cooperative evaluation
-            if s == 4 and (pr >= 2 or N > 4096):      # 4-CTA clusters: dense kernel, at most 4 x 1024 points
+            if s in (4, 44) and (pr >= 2 or N > 4096):      # 4-CTA clusters: dense kernel, at most 4 x 1024 points
                 continue
             assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s, prune=pr), two), "cluster size %d, prune %d" % (s, pr)
     big = pu.furthest_point_sample_features(x.repeat(6, 1, 1), f.repeat(6, 1, 1), 1.0, M)   # 18 clouds: the launcher's own pick
