@@ -264,11 +264,14 @@ def test_fused_ffps_adversarial_ties(ops, C, M, kind):
             assert torch.equal(pu.furthest_point_sample_features(x, f, 1.0, M, cluster_size=s), two), "cluster size %d" % s
 
 
-@pytest.mark.parametrize("N,kind", [(4096, "dup"), (4096, "equal_features"), (3600, "plain"), (4224, "plain"), (4100, "dup")])
+@pytest.mark.parametrize("N,kind", [(4096, "dup"), (4096, "equal_features"), (3600, "plain"), (4224, "plain"), (4100, "dup"),
+                                    (3073, "plain_bnc"), (4095, "dup_bnc")])
 def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
     """The 4-CTA (1024 points per CTA, half of the channels read from shared memory), 6-CTA (704 points per CTA, uneven last slice) and 8-CTA cluster forms of the fused F-FPS kernel pick the same
     indices as the two-call path, ties included (the launcher chooses between them by batch size; forced here)."""
     pu = ops[0]
+    bnc = kind.endswith("_bnc")          # point-major features (B, N, C) instead of the permuted view of (B, C, N)
+    kind = kind.replace("_bnc", "")
     B, C, M = 3, 64, 1024 if kind == "dup" else 300
     rng = np.random.default_rng(N)
     xyz = synth.clouds(B, N, seed=11, dup_frac=0.3 if kind == "dup" else 0.0)
@@ -278,7 +281,7 @@ def test_fused_ffps_cluster_sizes_agree(ops, monkeypatch, N, kind):
         feats[:, :, dst] = feats[:, :, src]; xyz[:, dst] = xyz[:, src]
     elif kind == "equal_features":
         feats[:] = 1.0
-    x, f = cu(xyz), cu(feats).permute(0, 2, 1)
+    x, f = cu(xyz), (cu(np.ascontiguousarray(feats.transpose(0, 2, 1))) if bnc else cu(feats).permute(0, 2, 1))
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(x, f, 1.0), M)
     for s in (4, 44, 6, 8):    # 44: 4-CTA clusters with four points per thread
         for pr in (1, 2, 3):   # dense / pruned / pruned with cooperative evaluation
@@ -363,11 +366,13 @@ def test_fused_ffps_pruned_non_finite(ops, kind):
         assert torch.equal(res[0][1].nan_to_num(nan=-7.0), r[1].nan_to_num(nan=-7.0))
 
 
-def test_fused_ffps_full_batch(ops):
-    """Layer-2 shape of the chain at batch 16 (more clusters than fit at once: several waves)."""
+@pytest.mark.parametrize("B", [16, 48])
+def test_fused_ffps_full_batch(ops, B):
+    """Layer-2 shape of the chain at batch 16 (one wave of 6-CTA clusters) and 48 (the launcher's 4-CTA form, four points per
+    thread, more clusters than fit at once: two waves)."""
     pu = ops[0]
-    xyz = cu(synth.clouds(16, 4096, seed=8))
-    f = cu(synth.features(16, 64, 4096, seed=8)).permute(0, 2, 1)
+    xyz = cu(synth.clouds(B, 4096, seed=8))
+    f = cu(synth.features(B, 64, 4096, seed=8)).permute(0, 2, 1)
     got = pu.furthest_point_sample_features(xyz, f, 1.0, 512)
     two = pu.furthest_point_sample_matrix(pu.calc_dist_matrix_for_sampling(xyz, f, 1.0), 512)
     assert torch.equal(got, two)
