@@ -550,10 +550,29 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                 if (ew == b) { ev = 0u; ew = 0xffffffffu; }
             }
             // ---- accept the longest prefix that is provably the reference sequence ----
+            // Branch-free: the coordinates of all SPECK candidates are fetched at once, every pairwise test is evaluated, and the
+            // prefix length falls out of a chain of ANDs.  (A candidate is only ever tested against the candidates ranked before
+            // it, which are exactly the accepted ones when its turn comes, so testing against c_i instead of "accepted q_i" is
+            // the same predicate.  The sequential form -- load, test, branch per candidate -- was 11 % of the kernel's stall
+            // samples.)
             const int limit = min(SPECK, m - it);
             if (cv[0] > ORD_M1) {
-                const uint32_t p0 = cw[0] & 0x3fffu;
-                qx[0] = lds_f32(sx_s + p0 * 4u); qy[0] = lds_f32(sy_s + p0 * 4u); qz[0] = lds_f32(sz_s + p0 * 4u);
+                float cx[SPECK], cy[SPECK], cz[SPECK];
+#pragma unroll
+                for (int j = 0; j < SPECK; ++j) {
+                    const uint32_t pj = cw[j] == 0xffffffffu ? 0u : (cw[j] & 0x3fffu);      // an absent candidate (value 0, word ~0) reads slot 0 and is never accepted
+                    cx[j] = lds_f32(sx_s + pj * 4u); cy[j] = lds_f32(sy_s + pj * 4u); cz[j] = lds_f32(sz_s + pj * 4u);
+                }
+                bool okj[SPECK];
+                okj[0] = true;
+#pragma unroll
+                for (int j = 1; j < SPECK; ++j) {
+                    const float tj = ord2f(cv[j]);
+                    bool ok = j < limit && cv[j] > bound && tj > 0.f;
+#pragma unroll
+                    for (int i = 0; i < j; ++i) ok = ok && !(sqdist(cx[j], cy[j], cz[j], cx[i], cy[i], cz[i]) < tj);
+                    okj[j] = ok;
+                }
                 A = 1;
                 bool go = true;
 #pragma unroll
@@ -563,24 +582,14 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                         if (!(j < limit)) ++st_limit;
                         else if (!(cv[j] > bound)) ++st_bound;
                         else if (!(ord2f(cv[j]) > 0.f)) ++st_zero;
+                        else if (!okj[j]) ++st_pair;
                     }
 #endif
-                    if (go && j < limit && cv[j] > bound && ord2f(cv[j]) > 0.f) {
-                        const uint32_t pj = cw[j] & 0x3fffu;
-                        const float cx = lds_f32(sx_s + pj * 4u), cy = lds_f32(sy_s + pj * 4u), cz = lds_f32(sz_s + pj * 4u);
-                        const float tj = ord2f(cv[j]);
-                        bool ok = true;
-#pragma unroll
-                        for (int i = 0; i < j; ++i) ok = ok && !(sqdist(cx, cy, cz, qx[i], qy[i], qz[i]) < tj);
-                        if (ok) { qx[j] = cx; qy[j] = cy; qz[j] = cz; A = j + 1; }
-                        else go = false;
-#ifdef DE6D_FPS_STATS
-                        if (!ok) ++st_pair;
-#endif
-                    } else {
-                        go = false;
-                    }
+                    go = go && okj[j];
+                    if (go) A = j + 1;
                 }
+#pragma unroll
+                for (int j = 0; j < SPECK; ++j) { qx[j] = cx[j]; qy[j] = cy[j]; qz[j] = cz[j]; }   // entries >= A are never read
                 if (tid == 0) {
 #pragma unroll
                     for (int j = 0; j < SPECK; ++j)

@@ -28,7 +28,7 @@ for rep in sys.argv[1:]:
         return float(v.replace(",", "")) if v not in ("", "n/a") else 0.0
 
     want = {"de6d_furthest_point_sampling": "fps_", "de6d_furthest_point_sampling_weights": "fps_",
-            "de6d_furthest_point_sampling_features": "fps_features_kernel", "de6d_furthest_point_sampling_matrix": "fps_matrix_kernel"}
+            "de6d_furthest_point_sampling_features": "fps_features", "de6d_furthest_point_sampling_matrix": "fps_matrix_kernel"}
     fps_launches = [d for d in launches if "fps_" in d["Kernel Name"]]
     pos = 0
     for entry, shape in trace:

@@ -17,7 +17,7 @@ def kernels_of(entry, shape):
     if entry in ("de6d_furthest_point_sampling", "de6d_furthest_point_sampling_weights"):
         return ["fps_"]
     if entry == "de6d_furthest_point_sampling_features":
-        return ["fps_features_kernel"]
+        return ["fps_features"]
     if entry == "de6d_furthest_point_sampling_matrix":
         return ["fps_matrix_kernel"]
     if entry == "de6d_dist_matrix":
