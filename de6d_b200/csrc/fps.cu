@@ -439,13 +439,16 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
 #pragma unroll
         for (int i = 1; i < SPECK; ++i) { qx[i] = x1; qy[i] = y1; qz[i] = z1; }
         // one pass over the buckets a pending sample can change: min-distances, bucket maximum / second / bound
-        auto update_pass = [&](int na) {
+        // The pending samples always fill all SPECK slots: slots beyond the accepted prefix repeat the round's first sample (a
+        // minimum over a set with a repeated element is the same minimum), so neither the bounds nor the visits need a per-slot
+        // "is this slot live" branch.
+        auto update_pass = [&]() {
             bool act = false;
             if (lane < BPW) {
                 float lb = bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, qx[0], qy[0], qz[0]);
 #pragma unroll
                 for (int i = 1; i < SPECK; ++i)
-                    if (i < na) lb = fminf(lb, bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, qx[i], qy[i], qz[i]));
+                    lb = fminf(lb, bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, qx[i], qy[i], qz[i]));
                 act = prune ? (lb < bmaxt) : (((lane * NW + w) << 5) < n);
             }
             unsigned mask = __ballot_sync(0xffffffffu, act);
@@ -485,10 +488,10 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                 float d0 = sqdist(x0, y0, z0, qx[0], qy[0], qz[0]), d1 = sqdist(x1, y1, z1, qx[0], qy[0], qz[0]);
 #pragma unroll
                 for (int i = 1; i < SPECK; ++i)
-                    if (i < na) {
-                        d0 = fminf(sqdist(x0, y0, z0, qx[i], qy[i], qz[i]), d0);
-                        d1 = fminf(sqdist(x1, y1, z1, qx[i], qy[i], qz[i]), d1);
-                    }
+                {
+                    d0 = fminf(sqdist(x0, y0, z0, qx[i], qy[i], qz[i]), d0);
+                    d1 = fminf(sqdist(x1, y1, z1, qx[i], qy[i], qz[i]), d1);
+                }
                 const float t0 = touch(j0, d0);
                 float t1 = t0;
                 if (two) t1 = touch(j1, d1);
@@ -518,7 +521,7 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         unsigned long long st_rounds = 0, st_acc = 0, st_bound = 0, st_pair = 0, st_limit = 0, st_zero = 0, st_full = 0;
 #endif
         while (it < m) {
-            update_pass(A);
+            update_pass();
             // ---- this warp's two best bucket maxima + the largest value it does not report ----
             uint32_t a1 = bval, b1 = bword;
             warp_argmax(a1, b1);
@@ -589,14 +592,24 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                     if (go) A = j + 1;
                 }
 #pragma unroll
-                for (int j = 0; j < SPECK; ++j) { qx[j] = cx[j]; qy[j] = cy[j]; qz[j] = cz[j]; }   // entries >= A are never read
-                if (tid == 0) {
+                for (int j = 0; j < SPECK; ++j) {      // slots beyond the accepted prefix repeat sample 0
+                    const bool live = j < A;
+                    qx[j] = live ? cx[j] : cx[0]; qy[j] = live ? cy[j] : cy[0]; qz[j] = live ? cz[j] : cz[0];
+                }
+                // warp j records sample j: one warp writing all of them was SPECK index decodes behind every other warp at the
+                // next barrier
+                static_assert(SPECK <= NW, "one warp per recorded sample");
+                if (lane == 0 && w < A) {
+                    uint32_t cwj = cw[0];
 #pragma unroll
-                    for (int j = 0; j < SPECK; ++j)
-                        if (j < A) idxs[it + j] = (int)index_of_cprio(cw[j] >> 14, log2B, ibits);
+                    for (int j = 1; j < SPECK; ++j)
+                        if (w == j) cwj = cw[j];
+                    idxs[it + w] = (int)index_of_cprio(cwj >> 14, log2B, ibits);
                 }
             } else {   // nothing exceeds -1: the reference selects index 0
                 qx[0] = lds_f32(sx_s + pos0 * 4u); qy[0] = lds_f32(sy_s + pos0 * 4u); qz[0] = lds_f32(sz_s + pos0 * 4u);
+#pragma unroll
+                for (int j = 1; j < SPECK; ++j) { qx[j] = qx[0]; qy[j] = qy[0]; qz[j] = qz[0]; }
                 A = 1;
                 if (tid == 0) idxs[it] = 0;
             }
@@ -613,7 +626,12 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
         }
 #endif
         // the reference applies every sample's update except the last one's: catch up on the final round
-        if (A > 1) update_pass(A - 1);
+        if (A > 1) {
+#pragma unroll
+            for (int j = 1; j < SPECK; ++j)
+                if (j >= A - 1) { qx[j] = qx[0]; qy[j] = qy[0]; qz[j] = qz[0]; }
+            update_pass();
+        }
     } else {
     for (int it = first_it; it < m; ++it) {
             bool act = false;
