@@ -21,6 +21,13 @@ __device__ __forceinline__ float sqdist(float ax, float ay, float az, float bx, 
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// Two squared distances at once on the packed-fp32 pipe (sm_100 FADD2 / FMUL2 / FFMA2): the points (a.x, a.y) against ONE
+// point b, lane-wise the same IEEE operations as sqdist() above (a + (-b) rounds like a - b), hence the same bits.
+__device__ __forceinline__ float2 sqdist2(float2 ax, float2 ay, float2 az, float bx, float by, float bz) {
+    const float2 dx = __fadd2_rn(ax, make_float2(-bx, -bx)), dy = __fadd2_rn(ay, make_float2(-by, -by)), dz = __fadd2_rn(az, make_float2(-bz, -bz));
+    return __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+}
+
 // Monotone map float -> uint32 (total order of finite floats, -0 < +0).
 __device__ __forceinline__ uint32_t f2ord(float f) {
     uint32_t u = __float_as_uint(f);
@@ -87,6 +94,18 @@ __device__ __forceinline__ float bucket_lower_bound(float lox, float hix, float 
     float gy = fmaxf(fmaxf(__fsub_rn(loy, qy), __fsub_rn(qy, hiy)), 0.f);
     float gz = fmaxf(fmaxf(__fsub_rn(loz, qz), __fsub_rn(qz, hiz)), 0.f);
     return __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+}
+
+// The same bound for TWO query points at once (packed fp32): lane-wise the operations of bucket_lower_bound.
+__device__ __forceinline__ float2 bucket_lower_bound2(float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                                      float2 qx, float2 qy, float2 qz) {
+    const float2 ax = __fadd2_rn(make_float2(lox, lox), make_float2(-qx.x, -qx.y)), bx = __fadd2_rn(qx, make_float2(-hix, -hix));
+    const float2 ay = __fadd2_rn(make_float2(loy, loy), make_float2(-qy.x, -qy.y)), by = __fadd2_rn(qy, make_float2(-hiy, -hiy));
+    const float2 az = __fadd2_rn(make_float2(loz, loz), make_float2(-qz.x, -qz.y)), bz = __fadd2_rn(qz, make_float2(-hiz, -hiz));
+    const float2 gx = make_float2(fmaxf(fmaxf(ax.x, bx.x), 0.f), fmaxf(fmaxf(ax.y, bx.y), 0.f));
+    const float2 gy = make_float2(fmaxf(fmaxf(ay.x, by.x), 0.f), fmaxf(fmaxf(ay.y, by.y), 0.f));
+    const float2 gz = make_float2(fmaxf(fmaxf(az.x, bz.x), 0.f), fmaxf(fmaxf(az.y, bz.y), 0.f));
+    return __ffma2_rn(gz, gz, __ffma2_rn(gx, gx, __fmul2_rn(gy, gy)));
 }
 
 // ---- TMA bulk copy + mbarrier + streaming access helpers (group_gather.cu, interpolate.cu) ----------------------
