@@ -726,7 +726,8 @@ def run_gpu_arm(args):
             cfg2, b2 = config_of(a2)
             try:
                 p2 = 8 if name == "chain16" else 4      # enough independent chains in flight to fill the SMs the sampling kernels leave idle
-                r2 = ChainRunner(cfg2, b2, dev, p2, rank, world)
+                # several chains in flight: the SM-time per cloud, not one launch's latency, is what counts -> 4-CTA F-FPS clusters
+                r2 = ChainRunner(cfg2, b2, dev, p2, rank, world, ffps_cluster=44)
                 ms2 = r2.resident(10, 3)
                 ms2_e2e = r2.e2e(10, ch.OpChain.SENSOR_KEYS)
                 r1 = ChainRunner(cfg2, b2, dev, 1, rank, world)

@@ -117,7 +117,7 @@ class OpChain:
 
     def __init__(self, cfg: ChainConfig, batch: int, device: Optional[torch.device] = None, use_graph: bool = True,
                  keep_matrices: bool = False, serial: bool = False, fused_group: bool = True,
-                 fused_ffps: bool = True, ffps: Optional[str] = None, shared_grid: bool = True):
+                 fused_ffps: bool = True, ffps: Optional[str] = None, shared_grid: bool = True, ffps_cluster: int = 0):
         self.cfg, self.batch = cfg, batch
         self.keep_matrices = keep_matrices   # tests: expose the F-FPS distance matrices fed to the kernel
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -128,6 +128,10 @@ class OpChain:
         # fp32 GEMM-expansion metric, bit-identical indices to the reference on the same GPU)
         self.ffps = ffps or ("fused" if fused_ffps else "matrix")
         self.shared_grid = shared_grid
+        # thread-block cluster form of the fused F-FPS kernel: 0 = the launcher's choice (least time for ONE launch of this batch);
+        # 44 = 4-CTA clusters regardless (least SM-time per cloud: what pays when several chains are in flight and the SMs, not
+        # one launch's latency, are the limit -- e.g. 16-frame batches); identical indices either way
+        self.ffps_cluster = ffps_cluster
         self._grids = {}
         self.main = torch.cuda.Stream(self.device)
         if serial:   # everything on one stream (per-kernel timing pass of bench.py, ncu launch lists)
@@ -235,7 +239,8 @@ class OpChain:
                         elif method == "f-fps":
                             f_slice = feats[:, :, lo:hi].permute(0, 2, 1)
                             if self.ffps == "fused" and not self.keep_matrices:
-                                sidx = pu.furthest_point_sample_features(xyz_slice, f_slice, cfg.ffps_gamma, npnt)
+                                cl = self.ffps_cluster if (self.ffps_cluster and f_slice.size(2) == 64 and 3072 < xyz_slice.size(1) <= 4096) else 0
+                                sidx = pu.furthest_point_sample_features(xyz_slice, f_slice, cfg.ffps_gamma, npnt, cluster_size=cl)
                             elif self.ffps == "cdist":   # exactly the reference's call pair (pointnet2_modules.py:383-388)
                                 mat = torch.cdist(xyz_slice, xyz_slice)
                                 mat += torch.cdist(f_slice, f_slice) * cfg.ffps_gamma
