@@ -777,7 +777,7 @@ def main():
     ap.add_argument("--config", default="chain64", choices=sorted(CONFIGS), help="BASELINE.json workload (default: configs[2])")
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (default: the config's)")
     ap.add_argument("--no-extras", action="store_true", help="skip reference_cuda / other_configs / reference-route legs")
-    ap.add_argument("--pipeline", type=int, default=6, help="independent chains in flight (1 = strictly serial steps)")
+    ap.add_argument("--pipeline", type=int, default=8, help="independent chains in flight (1 = strictly serial steps)")
     ap.add_argument("--impl", default="de6d_b200", choices=["de6d_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
