@@ -125,6 +125,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+    // the spin loop lives inside one asm block, so the compiler places no reconvergence point behind it: make the lanes
+    // meet again explicitly before anything warp-synchronous (REDUX, bar.sync) follows
+    __syncwarp();
 }
 // 1-D TMA bulk copy global -> shared (SASS: UBLKCP); bytes and both addresses must be multiples of 16.
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
