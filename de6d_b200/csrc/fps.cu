@@ -765,7 +765,13 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
             temp_g[index_of_cprio(cp, log2B, ibits)] = temp[j];
         }
     }
-    if (CL) cooperative_groups::this_cluster().sync();   // no CTA exits while a peer may still address its shared memory
+    if (CL) {
+        cooperative_groups::this_cluster().sync();   // no CTA exits while a peer may still address its shared memory
+        if (tid == 0) {      // invalidate the barrier objects: the next CTA on this SM initialises new ones at the same addresses
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_s) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_s + 8u) : "memory");
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -89,7 +89,11 @@ group_staged_kernel(int c, int n, long long ms, int G, int n_pad, long long chun
         }
     }
     if (plain || !TMA) __syncthreads();   // `plain` is uniform over the CTA
-    if (TMA) mbar_wait(bar, 0);
+    if (TMA) {
+        mbar_wait(bar, 0);
+        __syncthreads();                       // every thread is past the wait: the barrier object is dead from here on
+        if (threadIdx.x == 0) mbar_inval(bar);
+    }
 
     const long long j0 = (long long)blockIdx.x * chunk;
     const long long j1 = min(ms, j0 + chunk);

@@ -104,6 +104,8 @@ three_interpolate_staged_kernel(int c, int m, int n, int G, int m_pad, int chunk
         for (int g = 0; g < g_here; ++g) tma_bulk_g2s(rows + (size_t)g * m_pad, src + (size_t)g * m, (uint32_t)m * 4u, bar);
     }
     mbar_wait(bar, 0);
+    __syncthreads();                           // every thread is past the wait: the barrier object is dead from here on
+    if (threadIdx.x == 0) mbar_inval(bar);
 
     const int q0 = blockIdx.x * chunk, q1 = min(n, q0 + chunk);
     const int *ix = idx + (size_t)bs * n * 3;

@@ -379,6 +379,7 @@ sa_mlp_kernel(const SaMlpParams p) {
     if ((!ok || s_fail) && p.status && tid == 0) atomicExch(p.status, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     tile_sync();
+    if (tid == 0) { mbar_inval(&bar_w); mbar_inval(&bar_mma); }     // nothing can arrive on them any more
     if (warp == 0) {
         if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(p.tmem_cols));
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(p.tmem_cols));
