@@ -463,7 +463,9 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                     for (int i = 1; i < SPECK; ++i)
                         lb = fminf(lb, bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, qx[i], qy[i], qz[i]));
                 }
-                act = prune ? (lb < bmaxt) : (((lane * NW + w) << 5) < n);
+                // lb < (largest min-distance of the bucket), compared on the order-preserving integer images: the bucket maximum is
+                // cached as bval = f2ord(max) (0 = empty bucket, below every image of a lower bound >= +0), so no float copy of it is kept
+                act = prune ? (f2ord(lb) < bval) : (((lane * NW + w) << 5) < n);
             }
             unsigned mask = __ballot_sync(0xffffffffu, act);
             // Visit the active buckets two at a time.  Only the access to the bucket's min-distance register needs the bucket
@@ -528,8 +530,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                 const uint32_t below1 = __reduce_max_sync(0xffffffffu, top1 ? 0u : v_own1);
                 const uint32_t sec0 = __popc(__ballot_sync(0xffffffffu, top0)) > 1 ? v0 : below0;
                 const uint32_t sec1 = __popc(__ballot_sync(0xffffffffu, top1)) > 1 ? v1 : below1;
-                if (lane == j0) { bval = v0; bword = wd0; bmaxt = v0 ? ord2f(v0) : -INFINITY; bval2 = sec0; }
-                if (two && lane == j1) { bval = v1; bword = wd1; bmaxt = v1 ? ord2f(v1) : -INFINITY; bval2 = sec1; }
+                if (lane == j0) { bval = v0; bword = wd0; bval2 = sec0; }
+                if (two && lane == j1) { bval = v1; bword = wd1; bval2 = sec1; }
             }
         };
         const uint32_t wq_s = (uint32_t)__cvta_generic_to_shared(wq), bq_s = (uint32_t)__cvta_generic_to_shared(bq);
