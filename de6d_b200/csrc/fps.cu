@@ -658,7 +658,8 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
             if (lane < BPW) {
                 if (prune) {
                     float lb = bucket_lower_bound(blox, bhix, bloy, bhiy, bloz, bhiz, x1, y1, z1);
-                    act = lb < bmaxt;
+                    // D-FPS: the bucket maximum is bval = f2ord(max) itself, compare the integer images (as in the multi-sample path)
+                    act = MODE == FPS_D ? (f2ord(lb) < bval) : (lb < bmaxt);
                 } else {
                     act = ((lane * NW + w) << 5) < n;
                 }
@@ -684,7 +685,10 @@ fps_bucket_kernel(int n_in, int m, int log2B, int ibits, const float *__restrict
                     if (MODE == FPS_S) tm = __reduce_max_sync(0xffffffffu, (p < n) ? f2ord(t) : 0u);
                     warp_argmax(v, wd);
                     if (MODE == FPS_D) tm = v;
-                    if (lane == j) { bval = v; bword = wd; bmaxt = tm ? ord2f(tm) : -INFINITY; }
+                    if (lane == j) {
+                        bval = v; bword = wd;
+                        if (MODE == FPS_S) bmaxt = tm ? ord2f(tm) : -INFINITY;
+                    }
                 }
             };
             while (mask) {
