@@ -162,3 +162,25 @@ def test_small_cloud_fps_register_layout_is_the_reference_tie_order():
                 assert prio > last
                 last = prio
         assert seen == set(range(n))
+
+
+def test_kernel_form_planning_is_host_side():
+    """Shape planning of the cluster F-FPS kernels and of the fused SA scale runs on the host (no CUDA call): which shapes fit, how
+    an oversize last layer is split, and that bad selectors are refused before anything is launched."""
+    import ctypes as C
+    from de6d_b200 import _lib, sa_fused
+    lib = _lib.load()
+    fits = lib.de6d_furthest_point_sampling_features_fits
+    assert fits(4096, 64) == 1 and fits(3073, 64) == 1 and fits(512, 128) == 1
+    assert fits(130, 128) == 1            # only the pruned form covers few points with many channels
+    assert fits(0, 64) == 0 and fits(100000, 64) == 0 and fits(16384, 64) == 0
+    plan = sa_fused.FusedSAScale.plan
+    assert plan([4, 16, 16, 32], 32) == (1, 1)              # SA1: one CTA holds all weights
+    assert plan([131, 128, 128, 256], 32) == (2, 1)         # SA3 scale 1: a cta_group::2 pair
+    assert plan([131, 128, 256, 256], 32) == (2, 2)         # SA3 scale 3: the last layer in two launches
+    assert plan([259, 256, 256, 512], 16) == (0, 0)         # vote head: the first layers alone exceed an SM pair
+    assert plan([35, 24, 32], 32) == (0, 0) and plan([35, 32, 32], 24) == (0, 0)
+    null = C.c_void_p(0)
+    for cluster, prune in ((5, 0), (0, 4), (7, 1), (0, -1)):
+        rc = lib.de6d_furthest_point_sampling_features_impl(1, 4096, 64, 8, null, null, 0, 0, 0, 1.0, null, null, cluster, prune, null)
+        assert rc == 1 and b"must be" in lib.de6d_last_error_string()
